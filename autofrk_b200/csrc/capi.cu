@@ -1,0 +1,255 @@
+// C ABI (include/frk_b200.h).  No exception crosses this boundary: everything is converted to
+// (status, thread-local message) -- the C analogue of BEGIN_RCPP/END_RCPP (src/RcppExports.cpp:18,24).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/frk_b200.h"
+#include "frk_common.cuh"
+#include "mrts_plan.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int32_t guarded(F&& f) {
+    try {
+        f();
+        return FRK_OK;
+    } catch (const frk::Error& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return FRK_EINTERNAL;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return FRK_EINTERNAL;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return FRK_EINTERNAL;
+    }
+}
+
+void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        frk::fail(FRK_ECUDA, "no CUDA device available (frk_b200 has no CPU fallback): %s",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+}
+
+}  // namespace
+
+struct frk_plan {
+    frk::MrtsPlan* mp = nullptr;
+    // resources of the host-buffer path (created lazily)
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    frk::DevBuf<double> dx, dbuf[2];
+    ~frk_plan() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
+        }
+        if (s_comp) cudaStreamDestroy(s_comp);
+        if (s_copy) cudaStreamDestroy(s_copy);
+        if (mp) frk::plan_destroy(mp);
+    }
+    void ensure_streams() {
+        if (s_comp) return;
+        FRK_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        FRK_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
+        }
+    }
+};
+
+namespace {
+
+frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, const double* UZ,
+                    int64_t uz_rows, int64_t uz_cols, const double* nconst, int32_t k, bool on_device) {
+    require_device();
+    if (d < 1 || d > 3) frk::fail(FRK_EINVAL, "Unsupported dimension d: %d", d);
+    if (n < 1) frk::fail(FRK_EINVAL, "n must be greater than 1");
+    if (uz_rows < n || uz_cols < k) frk::fail(FRK_EINVAL, "UZ dimensions are inconsistent with n and k");
+    if (k < 1) frk::fail(FRK_EINVAL, "k must be positive");
+    auto plan = new frk_plan();
+    try {
+        // colMeans(Xu): R/autoFRK.R:1462
+        std::vector<double> hXu(size_t(n) * d);
+        double shift[3] = {0, 0, 0};
+        frk::DevBuf<double> dXu, dB, dU;
+        const double *pXu = Xu, *pB = BBBH, *pU = UZ;
+        if (on_device) {
+            FRK_CUDA(cudaMemcpy(hXu.data(), Xu, sizeof(double) * n * d, cudaMemcpyDeviceToHost));
+        } else {
+            std::memcpy(hXu.data(), Xu, sizeof(double) * n * d);
+            dXu.alloc(size_t(n) * d);
+            dB.alloc(size_t(d + 1) * n);
+            dU.alloc(size_t(uz_rows) * k);
+            FRK_CUDA(cudaMemcpy(dXu.p, Xu, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+            FRK_CUDA(cudaMemcpy(dB.p, BBBH, sizeof(double) * (d + 1) * n, cudaMemcpyHostToDevice));
+            FRK_CUDA(cudaMemcpy(dU.p, UZ, sizeof(double) * uz_rows * k, cudaMemcpyHostToDevice));
+            pXu = dXu.p;
+            pB = dB.p;
+            pU = dU.p;
+        }
+        for (int c = 0; c < d; ++c) {
+            long double s = 0.0L;  // R's colMeans accumulates in long double
+            for (int64_t j = 0; j < n; ++j) s += hXu[j + size_t(c) * n];
+            shift[c] = double(s / (long double)n);
+        }
+        plan->mp = frk::plan_create_dev(pXu, n, d, pB, pU, uz_rows, k, nconst, shift, nullptr);
+    } catch (...) {
+        delete plan;
+        throw;
+    }
+    return plan;
+}
+
+void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, int32_t mode) {
+    if (mode != FRK_OUT_X1 && mode != FRK_OUT_BASIS) frk::fail(FRK_EINVAL, "unknown out_mode %d", mode);
+    if (n2 <= 0) return;
+    frk::MrtsPlan* mp = plan->mp;
+    plan->ensure_streams();
+    const int d = mp->d, k = mp->k;
+    // row chunks: two device buffers of <= ~512 MB each, a multiple of the tile height x SM count
+    const int64_t bm = mp->ki ? mp->ki->bm : 128;
+    int64_t rc = (int64_t(512) << 20) / (int64_t(k) * 8);
+    const int64_t wave = bm * mp->sm_count;
+    rc = std::max<int64_t>(wave, rc / wave * wave);
+    rc = std::min(rc, n2);
+    if (plan->dx.n < size_t(n2) * d) plan->dx.alloc(size_t(n2) * d);
+    for (int b = 0; b < 2; ++b)
+        if (plan->dbuf[b].n < size_t(rc) * k) plan->dbuf[b].alloc(size_t(rc) * k);
+    FRK_CUDA(cudaMemcpyAsync(plan->dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, plan->s_comp));
+    int c = 0;
+    for (int64_t r0 = 0; r0 < n2; r0 += rc, ++c) {
+        const int b = c & 1;
+        const int64_t rows = std::min(rc, n2 - r0);
+        if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(plan->s_comp, plan->ev_copy[b], 0));
+        if (mode == FRK_OUT_X1)
+            frk::plan_predict_x1_dev(mp, plan->dx.p + r0, rows, n2, plan->dbuf[b].p, rc, plan->s_comp);
+        else
+            frk::plan_predict_basis_dev(mp, plan->dx.p + r0, rows, n2, plan->dbuf[b].p, rc, plan->s_comp);
+        FRK_CUDA(cudaEventRecord(plan->ev_comp[b], plan->s_comp));
+        FRK_CUDA(cudaStreamWaitEvent(plan->s_copy, plan->ev_comp[b], 0));
+        FRK_CUDA(cudaMemcpy2DAsync(out + r0, sizeof(double) * n2, plan->dbuf[b].p, sizeof(double) * rc,
+                                   sizeof(double) * rows, size_t(k), cudaMemcpyDeviceToHost, plan->s_copy));
+        FRK_CUDA(cudaEventRecord(plan->ev_copy[b], plan->s_copy));
+    }
+    FRK_CUDA(cudaStreamSynchronize(plan->s_comp));
+    FRK_CUDA(cudaStreamSynchronize(plan->s_copy));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* frk_last_error(void) { return g_last_error.c_str(); }
+
+int32_t frk_version(void) { return 100; }
+
+int32_t frk_device_count(int32_t* count) {
+    return guarded([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        *count = n;
+    });
+}
+
+int32_t frk_set_device(int32_t device) {
+    return guarded([&] {
+        require_device();
+        FRK_CUDA(cudaSetDevice(device));
+    });
+}
+
+int32_t frk_plan_create(frk_plan** plan, const double* Xu, int64_t n, int32_t d, const double* BBBH,
+                        const double* UZ, int64_t uz_rows, int64_t uz_cols, const double* nconst, int32_t k,
+                        int32_t on_device) {
+    return guarded([&] {
+        if (!plan) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        *plan = nullptr;
+        *plan = make_plan(Xu, n, d, BBBH, UZ, uz_rows, uz_cols, nconst, k, on_device != 0);
+    });
+}
+
+int32_t frk_plan_destroy(frk_plan* plan) {
+    return guarded([&] { delete plan; });
+}
+
+int32_t frk_plan_info(const frk_plan* plan, int64_t info[8]) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        const frk::MrtsPlan* mp = plan->mp;
+        info[0] = mp->d;
+        info[1] = mp->m;
+        info[2] = mp->k;
+        info[3] = mp->k_compute;
+        info[4] = mp->ki ? mp->ki->bm : 0;
+        info[5] = mp->ki ? mp->ki->bn : 0;
+        info[6] = int64_t(mp->slices.size());
+        info[7] = mp->nchunks;
+    });
+}
+
+int64_t frk_plan_launches(const frk_plan* plan) { return (plan && plan->mp) ? plan->mp->launches : 0; }
+
+int32_t frk_plan_predict(frk_plan* plan, const double* xnew, int64_t n2, double* out, int32_t out_mode) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        predict_host(plan, xnew, n2, out, out_mode);
+    });
+}
+
+int32_t frk_plan_predict_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, double* d_out,
+                             int64_t ldo, int32_t out_mode, void* stream) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        if (ldx < n2 || ldo < n2) frk::fail(FRK_EINVAL, "leading dimensions must be >= n2");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (out_mode == FRK_OUT_X1)
+            frk::plan_predict_x1_dev(plan->mp, d_xnew, n2, ldx, d_out, ldo, st);
+        else if (out_mode == FRK_OUT_BASIS)
+            frk::plan_predict_basis_dev(plan->mp, d_xnew, n2, ldx, d_out, ldo, st);
+        else
+            frk::fail(FRK_EINVAL, "unknown out_mode %d", out_mode);
+    });
+}
+
+int32_t frk_mrtsrcpp_predict(const double* Xu, int64_t n, int32_t d, const double* xobs_diag, const double* xnew,
+                             int64_t n2, int32_t xnew_cols, const double* BBBH, int64_t bbbh_rows,
+                             int64_t bbbh_cols, const double* UZ, int64_t uz_rows, int64_t uz_cols,
+                             const double* nconst, int64_t nconst_len, int32_t k, double* X1) {
+    (void)xobs_diag;  // src/autoFRK.cpp:288: carried by the signature, never read
+    return guarded([&] {
+        // the reference's checks, in its order, with its messages (src/autoFRK.cpp:298-309, :114-116)
+        if (xnew_cols != d) frk::fail(FRK_EINVAL, "xnew must have %d columns", d);
+        if (bbbh_rows != d + 1 || bbbh_cols != n) frk::fail(FRK_EINVAL, "BBBH must be %d x %d", d + 1, int(n));
+        if (uz_rows < n || uz_cols < k) frk::fail(FRK_EINVAL, "UZ dimensions are inconsistent with n and k");
+        if (nconst_len != d) frk::fail(FRK_EINVAL, "nconst must have length %d", d);
+        if (d < 1 || d > 3) frk::fail(FRK_EINVAL, "Unsupported dimension d: %d", d);
+        if (n2 == 0 || k == 0) return;
+        frk_plan* plan = make_plan(Xu, n, d, BBBH, UZ, uz_rows, uz_cols, nconst, k, false);
+        try {
+            predict_host(plan, xnew, n2, X1, FRK_OUT_X1);
+        } catch (...) {
+            delete plan;
+            throw;
+        }
+        delete plan;
+    });
+}
+
+}  // extern "C"

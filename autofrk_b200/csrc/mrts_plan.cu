@@ -1,0 +1,224 @@
+// Plan construction (W packing, Cpoly, zero-column detection) and the K1 launch logic.
+#include <algorithm>
+#include <vector>
+#include "mrts_plan.cuh"
+
+namespace frk {
+
+namespace {
+
+// flags[c] = 1 if W[:, c] has any non-zero entry (W = UZ[0:m, 0:k], ld = ldu)
+__global__ void column_nonzero_kernel(const double* __restrict__ UZ, int64_t ldu, int64_t m, int k,
+                                      int* __restrict__ flags) {
+    const int c = blockIdx.x;
+    if (c >= k) return;
+    int any = 0;
+    for (int64_t j = threadIdx.x; j < m; j += blockDim.x) any |= (UZ[j + int64_t(c) * ldu] != 0.0);
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) flags[c] = any;
+}
+
+// Packed image of one slice: for every chunk of KC knots
+//   [q = 0..KC/4)[col = 0..BN)[t = 0..4)   W[chunk*KC + 4q + t][col0 + col]   (0 past m / past ncols)
+//   [kk = 0..KC)[c = 0..DP)                knot coordinates (knot 0 repeated past m: finite phi, W = 0)
+__global__ void pack_w_kernel(const double* __restrict__ UZ, int64_t ldu, const double* __restrict__ Xu,
+                              int64_t m, int d, int dp, int col0, int ncols, int bn, int kc, int nchunks,
+                              double* __restrict__ wpack) {
+    const int stage = kc * bn + kc * dp;
+    const int64_t total = int64_t(nchunks) * stage;
+    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+         idx += int64_t(gridDim.x) * blockDim.x) {
+        const int chunk = int(idx / stage);
+        const int r = int(idx % stage);
+        double v = 0.0;
+        if (r < kc * bn) {
+            const int q = r / (bn * 4), rem = r % (bn * 4);
+            const int col = rem >> 2, tt = rem & 3;
+            const int64_t j = int64_t(chunk) * kc + q * 4 + tt;
+            if (j < m && col < ncols) v = UZ[j + int64_t(col0 + col) * ldu];
+        } else {
+            const int rr = r - kc * bn;
+            const int kk = rr / dp, c = rr % dp;
+            int64_t j = int64_t(chunk) * kc + kk;
+            if (j >= m) j = 0;
+            if (c < d) v = Xu[j + int64_t(c) * m];
+        }
+        wpack[idx] = v;
+    }
+}
+
+// cpoly[a*bn + col] = sum_j BBBH[a, j] * W[j, col0+col]   (src/autoFRK.cpp:324, (BBBH) * UZ.block(0,0,n,k))
+__global__ void cpoly_kernel(const double* __restrict__ BBBH, const double* __restrict__ UZ, int64_t ldu,
+                             int64_t m, int d, int col0, int ncols, int bn, double* __restrict__ cpoly) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (d + 1) * bn) return;
+    const int a = idx / bn, col = idx % bn;
+    double s = 0.0;
+    if (col < ncols) {
+        const double* w = UZ + int64_t(col0 + col) * ldu;
+        for (int64_t j = 0; j < m; ++j) s = fma(BBBH[a + j * (d + 1)], w[j], s);
+    }
+    cpoly[idx] = s;
+}
+
+__global__ void zero_columns_kernel(double* out, int64_t ldo, int64_t n2, int c0, int c1) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n2) return;
+    for (int c = c0 + blockIdx.y; c < c1; c += gridDim.y) out[int64_t(c) * ldo + i] = 0.0;
+}
+
+// out[:,0] = 1, out[:,1+a] = (x[:,a] - shift[a]) / nconst[a]     R/autoFRK.R:1462-1464
+__global__ void poly_columns_kernel(const double* __restrict__ x, int64_t ldx, int64_t n2, int d, double s0,
+                                    double s1, double s2, double c0, double c1, double c2,
+                                    double* __restrict__ out, int64_t ldo) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n2) return;
+    out[i] = 1.0;
+    out[ldo + i] = (x[i] - s0) / c0;
+    if (d > 1) out[2 * ldo + i] = (x[i + ldx] - s1) / c1;
+    if (d > 2) out[3 * ldo + i] = (x[i + 2 * ldx] - s2) / c2;
+}
+
+const PredictKernelInfo* kernels_for(int d, int* count) {
+    switch (d) {
+        case 1: return predict_kernels_d1(count);
+        case 2: return predict_kernels_d2(count);
+        case 3: return predict_kernels_d3(count);
+    }
+    fail(1, "Unsupported dimension d: %d", d);  // src/autoFRK.cpp:114-116
+}
+
+}  // namespace
+
+MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBBBH, const double* dUZ,
+                          int64_t ldu, int k, const double* h_nconst, const double* h_shift,
+                          cudaStream_t st) {
+    if (d < 1 || d > 3) fail(1, "Unsupported dimension d: %d", d);
+    if (m < 1) fail(1, "n must be greater than 1");
+    if (k < 1) fail(1, "k must be positive");
+    auto* p = new MrtsPlan();
+    try {
+        FRK_CUDA(cudaGetDevice(&p->device));
+        FRK_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+        p->d = d;
+        p->m = m;
+        p->k = k;
+        if (h_nconst) {
+            for (int c = 0; c < d; ++c) p->nconst[c] = h_nconst[c];
+            p->has_nconst = true;
+        }
+        if (h_shift)
+            for (int c = 0; c < d; ++c) p->shift[c] = h_shift[c];
+
+        // trailing all-zero columns of W (R passes k = K; the last d+1 columns of UZ[0:m,] are zero,
+        // src/autoFRK.cpp:212-215, R/autoFRK.R:1458-1460) are not worth a DMMA
+        DevBuf<int> dflags(k);
+        column_nonzero_kernel<<<k, 256, 0, st>>>(dUZ, ldu, m, k, dflags.p);
+        FRK_CUDA(cudaGetLastError());
+        std::vector<int> flags(k);
+        FRK_CUDA(cudaMemcpyAsync(flags.data(), dflags.p, sizeof(int) * k, cudaMemcpyDeviceToHost, st));
+        FRK_CUDA(cudaStreamSynchronize(st));
+        int kc = k;
+        while (kc > 0 && !flags[kc - 1]) --kc;
+        p->k_compute = kc;
+        if (kc == 0) return p;  // nothing to project: X1 is identically zero
+
+        // kernel configuration: smallest padded slice width that holds the columns
+        int nk = 0;
+        const PredictKernelInfo* tab = kernels_for(d, &nk);
+        int max_bn = 0;
+        for (int i = 0; i < nk; ++i) max_bn = std::max(max_bn, tab[i].bn);
+        const int ntile8 = (kc + 7) / 8;
+        const int nslices = (ntile8 * 8 + max_bn - 1) / max_bn;
+        const int per_slice = ((ntile8 + nslices - 1) / nslices) * 8;  // columns per slice, multiple of 8
+        const PredictKernelInfo* best = nullptr;
+        for (int i = 0; i < nk; ++i)
+            if (tab[i].bn >= per_slice && (!best || tab[i].bn < best->bn || (tab[i].bn == best->bn && tab[i].bm > best->bm)))
+                best = &tab[i];
+        if (!best) fail(2, "internal: no K1 configuration for %d columns", per_slice);
+        p->ki = best;
+        best->prepare();
+        p->nchunks = int((m + best->kc - 1) / best->kc);
+
+        for (int s = 0; s < nslices; ++s) {
+            PredictSlice sl;
+            sl.col0 = s * per_slice;
+            sl.ncols = std::min(per_slice, kc - sl.col0);
+            if (sl.ncols <= 0) break;
+            sl.wpack.alloc(size_t(p->nchunks) * best->stage_doubles);
+            sl.cpoly.alloc(size_t(d + 1) * best->bn);
+            pack_w_kernel<<<p->sm_count * 4, 256, 0, st>>>(dUZ, ldu, dXu, m, d, best->dp, sl.col0, sl.ncols,
+                                                           best->bn, best->kc, p->nchunks, sl.wpack.p);
+            FRK_CUDA(cudaGetLastError());
+            const int nthr = (d + 1) * best->bn;
+            cpoly_kernel<<<(nthr + 127) / 128, 128, 0, st>>>(dBBBH, dUZ, ldu, m, d, sl.col0, sl.ncols, best->bn,
+                                                            sl.cpoly.p);
+            FRK_CUDA(cudaGetLastError());
+            p->slices.push_back(std::move(sl));
+        }
+        FRK_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete p;
+        throw;
+    }
+    return p;
+}
+
+void plan_destroy(MrtsPlan* p) { delete p; }
+
+// first `kout` columns of X1 into dout (columns past k_compute are exact zeros)
+static void predict_cols(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t ldx, double* dout, int64_t ldo,
+                         int kout, cudaStream_t st) {
+    if (n2 <= 0 || kout <= 0) return;
+    const int kc = std::min(kout, p->k_compute);
+    if (kc < kout) {
+        dim3 grid(unsigned((n2 + 255) / 256), unsigned(std::min(kout - kc, 64)));
+        zero_columns_kernel<<<grid, 256, 0, st>>>(dout, ldo, n2, kc, kout);
+        FRK_CUDA(cudaGetLastError());
+        ++p->launches;
+    }
+    if (kc == 0) return;
+    const PredictKernelInfo* ki = p->ki;
+    const int64_t ntiles = (n2 + ki->bm - 1) / ki->bm;
+    const int grid = int(std::min<int64_t>(ntiles, p->sm_count));
+    for (auto& sl : p->slices) {
+        const int ncols = std::min(sl.ncols, kc - sl.col0);
+        if (ncols <= 0) break;
+        PredictArgs a;
+        a.xnew = dxnew;
+        a.ldx = ldx;
+        a.n2 = n2;
+        a.wpack = sl.wpack.p;
+        a.nchunks = p->nchunks;
+        a.cpoly = sl.cpoly.p;
+        a.out = dout + int64_t(sl.col0) * ldo;
+        a.ldo = ldo;
+        a.ncols = ncols;
+        a.ntiles = ntiles;
+        ki->launch(a, grid, st);
+        FRK_CUDA(cudaGetLastError());
+        ++p->launches;
+    }
+}
+
+void plan_predict_x1_dev(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t ldx, double* dout, int64_t ldo,
+                         cudaStream_t st) {
+    predict_cols(p, dxnew, n2, ldx, dout, ldo, p->k, st);
+}
+
+void plan_predict_basis_dev(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t ldx, double* dout,
+                            int64_t ldo, cudaStream_t st) {
+    if (n2 <= 0) return;
+    if (!p->has_nconst) fail(1, "plan was created without nconst/shift: basis output unavailable");
+    const int kstar = p->k - p->d - 1;  // R/autoFRK.R:1449 (the plan's k is K = NCOL(object))
+    if (kstar < 0) fail(1, "k-1 can not be smaller than the number of dimensions!");
+    poly_columns_kernel<<<unsigned((n2 + 255) / 256), 256, 0, st>>>(dxnew, ldx, n2, p->d, p->shift[0], p->shift[1],
+                                                                   p->shift[2], p->nconst[0], p->nconst[1],
+                                                                   p->nconst[2], dout, ldo);
+    FRK_CUDA(cudaGetLastError());
+    ++p->launches;
+    // X1[, 1:kstar] lands right after the d+1 polynomial columns (R/autoFRK.R:1460,1466)
+    predict_cols(p, dxnew, n2, ldx, dout + int64_t(p->d + 1) * ldo, ldo, kstar, st);
+}
+
+}  // namespace frk

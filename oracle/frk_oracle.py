@@ -1,0 +1,395 @@
+"""numpy restatement of autoFRK's fixed-rank-kriging fit path (TEST INFRASTRUCTURE).
+
+PARITY UNPINNED (see oracle/__init__.py).  Follows, line by line:
+  src/autoFRK.cpp:24-32     getASCeigens       (Eigen SelfAdjointEigenSolver -> LAPACK dsyevd, ascending)
+  R/helper.R:12-26          getEigen, getHalf
+  R/autoFRK.R:333-397       cMLE   (incl. sol.v :335-351, sol.eta :352, neg2llik :353-362)
+  R/autoFRK.R:399-480       cMLEimat
+  R/autoFRK.R:845-852       invCz ;  R/helper.R:249-256 ZinvC (dead code upstream, restated for completeness)
+  R/helper.R:28-58          getLikelihood
+  R/autoFRK.R:199-331       selectBasis  (identity-D, no-NA 'fast' branch)
+  R/autoFRK.R:739-843       indeMLE      (isimat / no-NA branch -> cMLEimat)
+  R/autoFRK.R:121-197       autoFRK      (finescale = FALSE)
+  R/autoFRK.R:1168-1423     predict.FRK  (LKobj = NULL branches)
+`gram_stats` / `cmle_from_stats` are NOT in the reference: they restate cMLEimat as a function of
+(G, C, zz) only -- the algebra the CUDA path uses -- and are themselves checked against the
+literal restatement in tests/test_oracle.py.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+from .mrts_oracle import MrtsObject, mrts, predict_mrts, _as2d
+
+
+def getASCeigens(A):
+    """src/autoFRK.cpp:24-32: full symmetric eigendecomposition, ascending."""
+    w, V = sla.eigh(np.asarray(A, dtype=np.float64), driver="evd")
+    return {"value": w, "vector": V}
+
+
+def getEigen(A):
+    """R/helper.R:12-17: reverse to descending."""
+    obj = getASCeigens(A)
+    return {"value": obj["value"][::-1].copy(), "vector": obj["vector"][:, ::-1].copy()}
+
+
+def getHalf(Fk, iDFk):
+    """R/helper.R:19-26: (Fk' iDFk)^(-1/2), zero eigenvalues -> 0."""
+    dec = getEigen(np.asarray(Fk).T @ np.asarray(iDFk))       # :20  (full product, not syrk)
+    sroot = np.sqrt(np.maximum(dec["value"], 0.0))             # :22
+    with np.errstate(divide="ignore"):
+        sroot = np.where(sroot == 0, np.inf, sroot)            # :23
+        sroot = 1.0 / sroot                                    # :24
+    return dec["vector"] @ (sroot[:, None] * dec["vector"].T)  # :25
+
+
+def sol_v(d, s, trS, n):
+    """R/autoFRK.R:335-351 (identical copy at :400-416)."""
+    d = np.asarray(d, dtype=np.float64)
+    k = d.size
+    if d.max() < max(trS / n, s):
+        return max(trS / n - s, 0.0)
+    cumd = np.cumsum(d)
+    ks = np.arange(1, k + 1, dtype=np.float64)
+    if k == n:
+        ks[n - 1] = n - 1
+    pick = d > ((trS - cumd) / (n - ks))
+    L = int(np.max(np.nonzero(pick)[0])) + 1                   # 1-based max(which(pick))
+    if L == n:
+        L = n - 1
+    return max((trS - cumd[L - 1]) / (n - L) - s, 0.0)
+
+
+def sol_eta(d, s, v):
+    """R/autoFRK.R:352."""
+    return np.maximum(np.asarray(d) - s - v, 0.0)
+
+
+def neg2llik(d, s, v, trS, n):
+    """R/autoFRK.R:353-362."""
+    d = np.asarray(d, dtype=np.float64)
+    k = d.size
+    eta = np.maximum(d - s - v, 0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if np.max(eta / (s + v)) > 1e20:
+            return math.inf
+    return (n * math.log(2 * math.pi) + np.sum(np.log(eta + s + v)) + math.log(s + v) * (n - k)
+            + 1.0 / (s + v) * trS - 1.0 / (s + v) * np.sum(d * eta / (eta + s + v)))
+
+
+def _eigen_desc(A, k):
+    """R `eigen(A)` on a symmetric matrix: descending values, first k."""
+    w, V = sla.eigh(A)
+    return w[::-1][:k].copy(), V[:, ::-1][:, :k].copy()
+
+
+def cMLE(Fk, TT, trS, half, JSJ, s=0.0, ldet=None, wSave=False, onlylogLike=None, vfixed=None):
+    """R/autoFRK.R:333-397."""
+    if onlylogLike is None:
+        onlylogLike = not wSave
+    if ldet is None:
+        ldet = 0.0
+    Fk = np.asarray(Fk)
+    n, k = Fk.shape
+    d, P = _eigen_desc(JSJ, k)                                 # :368-370
+    v = sol_v(d, s, trS, n) if vfixed is None else vfixed      # :371-375
+    dii = np.maximum(d, 0.0)
+    dhat = sol_eta(dii, s, v)
+    if onlylogLike:
+        return {"negloglik": neg2llik(dii, s, v, trS, n) * TT + ldet * TT}  # :378-381
+    M = half @ P @ (dhat[:, None] * P.T) @ half                # :382
+    L = None
+    if wSave:
+        L = Fk @ ((np.sqrt(dhat)[:, None] * P.T) @ half).T     # :387
+        if np.all(dhat == 0):
+            dhat = dhat.copy()
+            dhat[0] = 0.1 ** 10                                # :388-390
+        L = L[:, dhat > 0]                                     # :391
+    return {"v": v, "M": M, "s": s, "negloglik": neg2llik(dii, s, v, trS, n) * TT + ldet * TT, "L": L}
+
+
+def invCz(R, L, z):
+    """R/autoFRK.R:845-852: (R + L L')^{-1} z by Woodbury.  R is a dense/diagonal n x n matrix or a
+    1-D vector holding its diagonal (the only forms the in-scope callers produce)."""
+    L = np.asarray(L, dtype=np.float64)
+    z = _as2d(z)
+    K = L.shape[1]
+    R = np.asarray(R, dtype=np.float64)
+    if R.ndim == 1:
+        iRZ = z / R[:, None]
+        iRL = L / R[:, None]
+        inner = np.linalg.solve(np.eye(K) + L.T @ iRL, L.T @ iRZ)
+        return iRZ - (L @ inner) / R[:, None]
+    iR = np.linalg.inv(R)                                      # :847
+    iRZ = iR @ z                                               # :848
+    right = L @ np.linalg.solve(np.eye(K) + L.T @ iR @ L, L.T @ iRZ)  # :849
+    return iRZ - iR @ right                                    # :851
+
+
+def ZinvC(R, L, z):
+    """R/helper.R:249-256 (never called upstream)."""
+    L = np.asarray(L, dtype=np.float64)
+    z = np.atleast_2d(np.asarray(z, dtype=np.float64))
+    K = L.shape[1]
+    iR = np.linalg.inv(np.asarray(R, dtype=np.float64))
+    ZiR = z @ iR
+    left = ZiR @ L @ np.linalg.inv(np.eye(K) + L.T @ iR @ L) @ L.T
+    return ZiR - left @ iR
+
+
+def cMLEimat(Fk, Data, s, wSave=False, S=None, onlylogLike=None):
+    """R/autoFRK.R:399-480 -- the literal sequence of n-sized products."""
+    if onlylogLike is None:
+        onlylogLike = not wSave
+    Fk = np.asarray(Fk, dtype=np.float64)
+    Data = _as2d(Data)
+    n, k = Fk.shape
+    TT = Data.shape[1]
+    trS = np.sum(np.sum(Data ** 2, axis=1)) / TT              # :431
+    half = getHalf(Fk, Fk)                                     # :432
+    ihF = half @ Fk.T                                          # :433
+    if S is None:
+        t = ihF @ Data
+        JSJ = (t @ t.T) / TT                                   # :435
+    else:
+        JSJ = (ihF @ S) @ ihF.T                                # :438
+    JSJ = (JSJ + JSJ.T) / 2                                    # :440
+    d, P = _eigen_desc(JSJ, k)                                 # :441-443
+    v = sol_v(d, s, trS, n)                                    # :444
+    dii = np.maximum(d, 0.0)
+    if onlylogLike:
+        return {"negloglik": neg2llik(dii, s, v, trS, n) * TT}
+    dhat = sol_eta(dii, s, v)                                  # :450
+    M = half @ P @ (dhat[:, None] * P.T) @ half                # :451
+    nll = neg2llik(dii, s, v, trS, n) * TT
+    if not wSave:
+        return {"v": v, "M": M, "s": s, "negloglik": nll}
+    L = Fk @ ((np.sqrt(dhat)[:, None] * P.T) @ half).T         # :459
+    if np.all(dhat == 0):
+        dhat = dhat.copy()
+        dhat[0] = 0.1 ** 10                                    # :460-462
+    L = L[:, dhat > 0]                                         # :463
+    invD = np.ones(n) / (s + v)                                # :464
+    iDZ = invD[:, None] * Data                                 # :465
+    KL = L.shape[1]
+    right = L @ (np.linalg.solve(np.eye(KL) + L.T @ (invD[:, None] * L), L.T @ iDZ))  # :466-467
+    INVtZ = iDZ - invD[:, None] * right                        # :468
+    etatt = M @ Fk.T @ INVtZ                                   # :469
+    GM = Fk @ M                                                # :470
+    V = M - GM.T @ invCz(np.full(n, s + v), L, GM)             # :471-474
+    return {"v": v, "M": M, "s": s, "negloglik": nll, "w": etatt, "V": V}
+
+
+# --------------------------------------------------------------------------------------------
+# (G, C, zz) restatement -- what the CUDA path evaluates
+# --------------------------------------------------------------------------------------------
+def gram_stats(Fk, Data):
+    """G = F'F (R/helper.R:20), C = F'Z, zz = sum(Z^2) (R/autoFRK.R:431)."""
+    Fk = np.asarray(Fk, dtype=np.float64)
+    Data = _as2d(Data)
+    return Fk.T @ Fk, Fk.T @ Data, float(np.sum(Data ** 2))
+
+
+def half_from_gram(G):
+    dec = getEigen(G)
+    sroot = np.sqrt(np.maximum(dec["value"], 0.0))
+    with np.errstate(divide="ignore"):
+        sroot = 1.0 / np.where(sroot == 0, np.inf, sroot)
+    return dec["vector"] @ (sroot[:, None] * dec["vector"].T)
+
+
+def cmle_from_stats(G, C, zz, n, TT, s=0.0, wSave=True):
+    """cMLEimat as a function of the sufficient statistics only.
+
+    ihF*Z = half*(F'Z) = half*C, so JSJ = (half C)(half C)'/T (R/autoFRK.R:433-435).  With
+    L'L = D^{1/2} P' half G half P D^{1/2} = diag(dhat) (half G half = I on the range of G):
+      w = half P diag(dhat/(s+v+dhat)) P' half C        (closed form of :464-469)
+      V = half P diag(dhat (s+v)/(s+v+dhat)) P' half    (closed form of :470-474)
+    """
+    k = G.shape[0]
+    trS = zz / TT
+    half = half_from_gram(G)
+    t = half @ C
+    JSJ = (t @ t.T) / TT
+    JSJ = (JSJ + JSJ.T) / 2
+    d, P = _eigen_desc(JSJ, k)
+    v = sol_v(d, s, trS, n)
+    dii = np.maximum(d, 0.0)
+    dhat = sol_eta(dii, s, v)
+    hP = half @ P
+    M = hP @ (dhat[:, None] * hP.T)
+    out = {"v": v, "M": M, "s": s, "negloglik": neg2llik(dii, s, v, trS, n) * TT}
+    if wSave:
+        sv = s + v
+        out["w"] = hP @ ((dhat / (sv + dhat))[:, None] * (hP.T @ C))
+        out["V"] = hP @ ((dhat * sv / (sv + dhat))[:, None] * hP.T)
+    return out
+
+
+def getLikelihood(Data, Fk, M, s, Depsilon_diag):
+    """R/helper.R:28-58 with a diagonal Depsilon (given as its diagonal)."""
+    Data = _as2d(Data)
+    Fk = np.asarray(Fk, dtype=np.float64)
+    O = ~np.isnan(Data)
+    TT = Data.shape[1]
+    n2loglik = O.sum() * math.log(2 * math.pi)                 # :38
+    Rdiag = s * np.asarray(Depsilon_diag, dtype=np.float64)    # :39
+    w, U = sla.eigh(M)                                         # :40
+    L = Fk @ U @ np.diag(np.sqrt(np.maximum(w, 0.0))) @ U.T    # :41-42
+    K = Fk.shape[1]
+    for tt in range(TT):
+        o = O[:, tt]
+        zt = Data[o, tt]
+        Rt = Rdiag[o]
+        Lt = L[o, :]
+        if Lt.shape[0] == 1:                                   # :48-51 (NCOL(Lt)==1 after drop)
+            n2loglik += math.log(Rt[0] + float(Lt @ Lt.T))
+        else:
+            sign, ld = np.linalg.slogdet(np.eye(K) + Lt.T @ (Lt / Rt[:, None]))
+            n2loglik += ld + np.sum(np.log(Rt)) + float(np.sum(zt * invCz(Rt, Lt, zt).ravel()))  # :53-54
+    return n2loglik
+
+
+# --------------------------------------------------------------------------------------------
+# model-fit orchestration (identity D, no missing values)
+# --------------------------------------------------------------------------------------------
+def _r_round(x):
+    """R's round(): IEC 60559 half-to-even, same as numpy."""
+    return np.round(x)
+
+
+def kgrid(d, maxK):
+    """Default K sequence, R/autoFRK.R:254-257."""
+    K = np.unique(_r_round(np.arange(d + 1, maxK + 1e-9, maxK ** (1.0 / 3) * d))).astype(int)
+    if K.size > 30:
+        K = np.unique(_r_round(np.linspace(d + 1, maxK, 30))).astype(int)
+    return K
+
+
+def selectBasis(Data, loc, maxK=None, Kseq=None, maxknot=5000, Fk=None):
+    """R/autoFRK.R:199-331, D = I, no NA, method='fast'."""
+    Data = _as2d(Data)
+    loc = _as2d(loc)
+    d = loc.shape[1]
+    N = Data.shape[0]
+    klim = int(min(N, _r_round(10 * math.sqrt(N))))            # :222
+    if N < maxknot:
+        knot = loc                                             # :223-224
+    else:
+        raise NotImplementedError("subKnot (R RNG) is out of scope")
+    if maxK is not None:
+        maxK = int(_r_round(maxK))
+    elif Kseq is not None:
+        maxK = int(_r_round(max(Kseq)))
+    else:
+        maxK = klim                                            # :228-236
+    if Kseq is not None:
+        K = np.array(sorted(set(int(_r_round(k)) for k in Kseq)))  # unique(round(Kseq))
+        if K.max() > maxK:
+            raise ValueError("maximum of Kseq is larger than maxK!")
+        K = K[K > d]
+        if K.size == 0:
+            raise ValueError("Not valid Kseq!")
+    else:
+        K = kgrid(d, maxK)                                     # :254-257
+    if Fk is None:
+        Fk = mrts(knot, int(K.max()), loc, maxknot)            # :260
+    F = Fk.X
+    TT = Data.shape[1]
+    iDFk = F                                                   # iD = I (:289-291)
+    trS = np.sum(np.sum(Data * Data, axis=1)) / TT             # :304
+    AIClist = np.full(K.size, np.inf)
+    for i, k in enumerate(K):
+        half = getHalf(F[:, :k], iDFk[:, :k])                  # :306
+        ihFiD = half @ iDFk[:, :k].T                           # :307
+        t = ihFiD @ Data
+        JSJ = (t @ t.T) / TT                                   # :308
+        JSJ = (JSJ + JSJ.T) / 2                                # :309
+        AIClist[i] = cMLE(F[:, :k], TT, trS, half, JSJ)["negloglik"]  # :310-316
+    df = np.where(K <= TT, K * (K + 1) / 2 + 1, K * TT + 1 - TT * (TT - 1) / 2)  # :321
+    AIClist = AIClist + 2 * df                                 # :322
+    Kopt = int(K[np.argmin(AIClist)])                          # :323
+    out = Fk.leading(Kopt)                                     # :324-328
+    out.extra["AIC"] = AIClist
+    out.extra["Kgrid"] = K
+    return out
+
+
+def indeMLE(Data, Fk, wSave=False, sigma=0.0):
+    """R/autoFRK.R:739-843, isimat & no-NA branch (:778-803)."""
+    Data = _as2d(Data)
+    if np.isnan(Data).any():
+        raise NotImplementedError("EM0miss path (missing data) is out of scope")
+    out = cMLEimat(np.asarray(Fk), Data, s=sigma, wSave=wSave)  # :787
+    if "v" in out:
+        out["s"] = out["v"] if sigma == 0 else sigma           # :788-795
+        del out["v"]
+    return out
+
+
+def autoFRK(Data, loc, mu=0.0, G=None, maxK=None, Kseq=None, maxknot=5000):
+    """R/autoFRK.R:121-197, finescale=FALSE, method='fast', D = I, no NA."""
+    Data = _as2d(Data) - mu                                    # :125
+    Fk = G if G is not None else selectBasis(Data, loc, maxK=maxK, Kseq=Kseq, maxknot=maxknot)  # :126-133
+    F = Fk.X if isinstance(Fk, MrtsObject) else np.asarray(Fk)
+    obj = indeMLE(Data, F, wSave=True)                         # :151
+    obj["G"] = Fk                                              # :185
+    obj["LKobj"] = None
+    return obj
+
+
+def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=None, mu_new=0.0,
+                se_report=False):
+    """R/autoFRK.R:1168-1423, LKobj = NULL, no missing-data attribute."""
+    if "w" not in obj:
+        raise ValueError('input model (object) should use the option "wsave=TRUE"!')
+    if newloc is None:
+        newloc = obsloc                                        # default newloc = obsloc
+    G = obj["G"]
+    Gmat = G.X if isinstance(G, MrtsObject) else np.asarray(G)
+    if basis is None:                                          # :1174-1188
+        if newloc is None and obsloc is None:
+            basis = Gmat
+        else:
+            if not isinstance(G, MrtsObject):
+                raise ValueError("Basis matrix of new locations should be given (unless the model was fitted with mrts bases)!")
+            basis = Gmat if newloc is None else predict_mrts(G, newloc)
+    basis = np.atleast_2d(np.asarray(basis, dtype=np.float64))
+    nobs = Gmat.shape[0] if obsloc is None else _as2d(obsloc).shape[0]
+    if obsData is not None:
+        obsData = np.asarray(obsData, dtype=np.float64).reshape(-1, 1) - mu_obs  # :1198
+        if obsData.size != nobs:
+            raise ValueError("Dimensions of obsloc and obsData are not compatible!")
+    if newloc is not None:
+        if basis.shape[0] != _as2d(newloc).shape[0]:
+            raise ValueError("Dimensions of newloc and basis are not compatible!")
+    elif basis.shape[0] != Gmat.shape[0]:
+        raise ValueError("Dimensions of obsloc and basis are not compatible!")
+    se = None
+    if obsloc is None and obsData is None:                     # :1214-1247
+        yhat = basis @ obj["w"]                                # :1216
+        if se_report:
+            TT = obj["w"].shape[1]
+            se = np.sqrt(np.maximum(0.0, np.sum((basis @ obj["V"]) * basis, axis=1)))  # :1220
+            se = np.repeat(se[:, None], TT, axis=1)            # :1222
+    if obsData is not None:                                    # :1248-1274
+        pick = np.nonzero(~np.isnan(obsData.ravel()))[0]
+        if obsloc is None:
+            Gp = Gmat[pick, :]
+        else:
+            Gp = predict_mrts(G, _as2d(obsloc)[pick, :])       # :1256
+        M = obj["M"]
+        GM = Gp @ M
+        w, U = sla.eigh(M)
+        w, U = w[::-1], U[:, ::-1]                             # R eigen(): descending
+        L = Gp @ U @ np.diag(np.sqrt(np.maximum(w, 0.0)))      # :1261-1264
+        Rd = np.full(pick.size, obj["s"])                      # s * De, De = I
+        yhat = basis @ GM.T @ invCz(Rd, L, obsData[pick])      # :1265-1268
+        if se_report:
+            V = M - GM.T @ invCz(Rd, L, GM)                    # :1270-1271
+            se = np.sqrt(np.maximum(0.0, np.sum((basis @ V) * basis, axis=1)))[:, None]  # :1272
+    return {"pred.value": yhat + mu_new, "se": se}

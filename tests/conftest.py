@@ -1,0 +1,24 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_libraries():
+    """The CUDA library and the C oracle are built in-tree (nvcc cross-compiles without a GPU)."""
+    from autofrk_b200 import build
+
+    if not build.LIB.exists() or os.environ.get("FRK_REBUILD"):
+        build.build_cuda()
+    build.build_oracle()
+    yield

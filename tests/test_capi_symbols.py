@@ -1,0 +1,49 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/frk_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "frk_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(frk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from autofrk_b200 import build
+
+    lib = ctypes.CDLL(str(build.LIB))
+    names = declared_symbols()
+    assert len(names) >= 10
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_header():
+    from autofrk_b200 import _lib
+
+    assert sorted(_lib._SIGNATURES) == declared_symbols()
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU every compute entry point must fail loudly (FRK_ECUDA), never compute on the CPU."""
+    import numpy as np
+    import pytest
+    from autofrk_b200 import _lib
+    from autofrk_b200 import mrts as G
+
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    Xu = np.random.default_rng(0).random((10, 2))
+    with pytest.raises(_lib.FrkError) as ei:
+        G.mrtsrcpp_predict(Xu, np.eye(2), Xu, np.zeros((3, 10)), np.zeros((13, 5)), np.ones(2), 2)
+    assert ei.value.code == _lib.FRK_ECUDA
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "autofrk_b200").rglob("*.py"):
+        src = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p

@@ -1,0 +1,119 @@
+"""K1 parity on the GPU: fused TPS evaluation + projection vs the oracle, through the C ABI.
+
+The fit (UZ, BBBH, nconst) comes from the oracle and is fed to both sides, which removes the
+eigenvector sign/rotation ambiguity.  Tolerance: 1e-10 column-max-relative."""
+import numpy as np
+import pytest
+
+from util import TOL, colrel, make_fit
+
+pytestmark = pytest.mark.gpu
+
+# (d, m, kstar, n2): cover every K1 slice configuration (BN 32..512, two slices), ragged rows / knots
+CASES = [
+    (2, 37, 4, 1),
+    (2, 64, 20, 7),
+    (2, 101, 28, 255),
+    (2, 150, 60, 1000),
+    (2, 200, 90, 1025),
+    (2, 250, 125, 777),
+    (2, 300, 160, 2049),
+    (2, 500, 197, 4000),
+    (2, 400, 250, 1500),
+    (2, 520, 300, 3001),
+    (2, 600, 380, 1999),
+    (2, 1000, 497, 5000),
+    (2, 801, 600, 1203),
+    (3, 90, 30, 513),
+    (3, 300, 100, 2000),
+    (3, 700, 520, 1500),
+    (1, 30, 8, 999),
+    (1, 40, 10, 31),
+]
+
+
+@pytest.mark.parametrize("d,m,kstar,n2", CASES)
+def test_mrtsrcpp_predict_matches_oracle(d, m, kstar, n2):
+    import oracle as O
+    from autofrk_b200 import mrts as G
+
+    Xu, xd, fit, rng = make_fit(d, m, kstar, seed=m + kstar)
+    xnew = rng.random((n2, d)) * 1.2 - 0.1
+    nk = min(n2, 5)
+    xnew[:nk] = Xu[:nk]                       # r == 0 hits (the `if (r != 0)` branch, src/autoFRK.cpp:137)
+    K = kstar + d + 1                          # what predict.mrts passes (R/autoFRK.R:1458)
+    ref = O.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], K)
+    got = G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], K)
+    assert got["X1"].shape == (n2, K)
+    assert np.all(got["X1"][:, kstar:] == 0.0)  # the d+1 trailing columns are exact zeros
+    err = colrel(got["X1"][:, :kstar], ref["X1"][:, :kstar])
+    assert err < TOL, err
+    assert got["X"] is not None and np.array_equal(got["X"], Xu)  # quirk: X = Xu (src/autoFRK.cpp:320)
+    # k = kstar (what mrtsrcpp_predict0 uses internally) gives the same columns
+    got2 = G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], kstar)
+    assert np.array_equal(got2["X1"], got["X1"][:, :kstar])
+
+
+def test_predict_mrts_basis_and_identity():
+    """predict.mrts end to end + the known-answer identity predict(mrts(knot,k), knot) == mrts(knot,k)."""
+    import oracle as O
+    from autofrk_b200 import mrts as G
+
+    d, m, kstar = 2, 300, 120
+    Xu, xd, fit, rng = make_fit(d, m, kstar, seed=5)
+    K = kstar + d + 1
+    oobj = O.MrtsObject(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    gobj = G.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    xnew = rng.random((1234, d))
+    ref = O.predict_mrts(oobj, xnew)
+    for use_plan in (True, False):
+        got = G.predict_mrts(gobj, xnew, use_plan=use_plan)
+        assert got.shape == (1234, K)
+        assert colrel(got, ref) < TOL
+    atk = G.predict_mrts(gobj, Xu)
+    assert colrel(atk[:, d + 1:], fit["X"][:, d + 1:]) < TOL
+    # column-subset object (selectBasis keeps the full UZ, R/autoFRK.R:324-328)
+    sub = gobj.leading(40)
+    refsub = O.predict_mrts(oobj.leading(40), xnew)
+    assert colrel(G.predict_mrts(sub, xnew), refsub) < TOL
+
+
+def test_error_messages_match_reference():
+    from autofrk_b200 import mrts as G
+    from autofrk_b200._lib import FrkError
+
+    d, m, kstar = 2, 50, 10
+    Xu, xd, fit, rng = make_fit(d, m, kstar, seed=1)
+    xnew = rng.random((10, d))
+    with pytest.raises(FrkError, match="xnew must have 2 columns"):
+        G.mrtsrcpp_predict(Xu, xd, rng.random((10, 3)), fit["BBBH"], fit["UZ"], fit["nconst"], kstar)
+    with pytest.raises(FrkError, match="BBBH must be 3 x 50"):
+        G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"][:, :-1], fit["UZ"], fit["nconst"], kstar)
+    with pytest.raises(FrkError, match="UZ dimensions are inconsistent with n and k"):
+        G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], 99)
+    with pytest.raises(FrkError, match="nconst must have length 2"):
+        G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"][:1], kstar)
+
+
+def test_predict_dev_torch_and_linearity():
+    """device-pointer path + a size-independent property at a larger n2: X1 is linear in W."""
+    import torch
+    from autofrk_b200 import mrts as G
+
+    d, m, kstar = 2, 500, 197
+    Xu, xd, fit, rng = make_fit(d, m, kstar, seed=2)
+    n2 = 300_000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xt = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=g).T   # column-major (n2, d)
+    plan = G.MrtsPlan(Xu, fit["BBBH"], fit["UZ"], fit["nconst"], kstar)
+    out = plan.predict_dev(xt)
+    torch.cuda.synchronize()
+    host = plan.predict(xt.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), host)          # same kernel, device vs host-buffer path
+    UZ2 = fit["UZ"].copy()
+    UZ2[:m, :kstar] *= 2.0                                    # exact in FP64
+    plan2 = G.MrtsPlan(Xu, fit["BBBH"], UZ2, fit["nconst"], kstar)
+    out2 = plan2.predict_dev(xt)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out * 2.0)
+    assert plan.launches > 0
