@@ -44,12 +44,27 @@ _SIGNATURES = {
     "frk_set_device": (_i32, [_i32]),
     "frk_mrtsrcpp_predict": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _vp, _i64, _i64,
                                     _vp, _i64, _i32, _vp]),
+    "frk_mrtsrcpp": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "frk_mrtsrcpp_predict0": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     _vp]),
+    "frk_getASCeigens": (_i32, [_vp, _i32, _vp, _vp]),
     "frk_plan_create": (_i32, [C.POINTER(_vp), _vp, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _i32, _i32]),
     "frk_plan_destroy": (_i32, [_vp]),
     "frk_plan_info": (_i32, [_vp, C.POINTER(_i64)]),
     "frk_plan_launches": (_i64, [_vp]),
     "frk_plan_predict": (_i32, [_vp, _vp, _i64, _vp, _i32]),
     "frk_plan_predict_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp]),
+    "frk_gram_stats": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "frk_gram_packed_len": (_i64, [_i32, _i32]),
+    "frk_gram_stats_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _vp, _vp]),
+    "frk_plan_predict_gram_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp]),
+    "frk_getHalf": (_i32, [_vp, _i64, _i32, _vp]),
+    "frk_cMLEimat_stats": (_i32, [_vp, _i64, _vp, _i64, C.c_double, _i32, _i32, _i64, C.c_double, _i32, _i32, _i32,
+                                  _vp, _vp, _vp, _vp, _vp]),
+    "frk_cMLE": (_i32, [_vp, _i64, _i32, _i32, C.c_double, _vp, _vp, C.c_double, C.c_double, _i32, _i32, _i32,
+                        C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "frk_plan_predict_frk": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "frk_basis_predict_frk": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
 }
 
 

@@ -1,35 +1,12 @@
 // C ABI (include/frk_b200.h).  No exception crosses this boundary: everything is converted to
 // (status, thread-local message) -- the C analogue of BEGIN_RCPP/END_RCPP (src/RcppExports.cpp:18,24).
-#include <algorithm>
-#include <cstring>
-#include <string>
-#include <vector>
-#include "../../include/frk_b200.h"
-#include "frk_common.cuh"
-#include "mrts_plan.cuh"
+#include "capi_internal.cuh"
 
-namespace {
+namespace frk_capi {
 
-thread_local std::string g_last_error;
-
-template <typename F>
-int32_t guarded(F&& f) {
-    try {
-        f();
-        return FRK_OK;
-    } catch (const frk::Error& e) {
-        g_last_error = e.what();
-        return e.code;
-    } catch (const std::bad_alloc&) {
-        g_last_error = "out of host memory";
-        return FRK_EINTERNAL;
-    } catch (const std::exception& e) {
-        g_last_error = e.what();
-        return FRK_EINTERNAL;
-    } catch (...) {
-        g_last_error = "unknown error";
-        return FRK_EINTERNAL;
-    }
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
 }
 
 void require_device() {
@@ -42,35 +19,17 @@ void require_device() {
     }
 }
 
-}  // namespace
+frk::GramWorkspace& gram_workspace() {
+    static thread_local frk::GramWorkspace ws;
+    return ws;
+}
 
-struct frk_plan {
-    frk::MrtsPlan* mp = nullptr;
-    // resources of the host-buffer path (created lazily)
-    cudaStream_t s_comp = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-    frk::DevBuf<double> dx, dbuf[2];
-    ~frk_plan() {
-        for (int i = 0; i < 2; ++i) {
-            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
-            if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
-        }
-        if (s_comp) cudaStreamDestroy(s_comp);
-        if (s_copy) cudaStreamDestroy(s_copy);
-        if (mp) frk::plan_destroy(mp);
-    }
-    void ensure_streams() {
-        if (s_comp) return;
-        FRK_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-        FRK_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            FRK_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-            FRK_CUDA(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
-        }
-    }
-};
+}  // namespace frk_capi
 
-namespace {
+using frk_capi::guarded;
+using frk_capi::require_device;
+
+namespace frk_capi {
 
 frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, const double* UZ,
                     int64_t uz_rows, int64_t uz_cols, const double* nconst, int32_t k, bool on_device) {
@@ -148,11 +107,14 @@ void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, i
     FRK_CUDA(cudaStreamSynchronize(plan->s_copy));
 }
 
-}  // namespace
+}  // namespace frk_capi
+
+using frk_capi::make_plan;
+using frk_capi::predict_host;
 
 extern "C" {
 
-const char* frk_last_error(void) { return g_last_error.c_str(); }
+const char* frk_last_error(void) { return frk_capi::last_error().c_str(); }
 
 int32_t frk_version(void) { return 100; }
 
@@ -249,6 +211,61 @@ int32_t frk_mrtsrcpp_predict(const double* Xu, int64_t n, int32_t d, const doubl
             throw;
         }
         delete plan;
+    });
+}
+
+static void fit_to_host(const frk::MrtsFitDev& f, double* X, double* UZ, double* BBBH, double* nconst) {
+    const int64_t m = f.m;
+    const int d = f.d, K = f.k + f.d + 1;
+    FRK_CUDA(cudaMemcpy(X, f.X.p, sizeof(double) * m * K, cudaMemcpyDeviceToHost));
+    FRK_CUDA(cudaMemcpy(UZ, f.UZ.p, sizeof(double) * (m + d + 1) * K, cudaMemcpyDeviceToHost));
+    FRK_CUDA(cudaMemcpy(BBBH, f.BBBH.p, sizeof(double) * (d + 1) * m, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < d; ++c) nconst[c] = f.nconst[c];
+}
+
+int32_t frk_mrtsrcpp(const double* Xu, int64_t n, int32_t d, const double* xobs_diag, int32_t xd_rows,
+                     int32_t xd_cols, int32_t k, double* X, double* UZ, double* BBBH, double* nconst) {
+    return guarded([&] {
+        if (xd_rows != d || xd_cols != d) frk::fail(FRK_EINVAL, "xobs_diag must be %d x %d", d, d);  // :231-233
+        require_device();
+        frk::MrtsFitDev f;
+        frk::mrts_fit_dev(Xu, xobs_diag, n, d, k, f);
+        fit_to_host(f, X, UZ, BBBH, nconst);
+    });
+}
+
+int32_t frk_mrtsrcpp_predict0(const double* Xu, int64_t n, int32_t d, const double* xobs_diag, int32_t xd_rows,
+                              int32_t xd_cols, const double* xnew, int64_t n2, int32_t xnew_cols, int32_t k,
+                              double* X, double* UZ, double* BBBH, double* nconst, double* X1) {
+    return guarded([&] {
+        if (xd_rows != d || xd_cols != d) frk::fail(FRK_EINVAL, "xobs_diag must be %d x %d", d, d);  // :257-259
+        if (xnew_cols != d) frk::fail(FRK_EINVAL, "xnew must have %d columns", d);                     // :260-262
+        require_device();
+        frk::MrtsFitDev f;
+        frk::mrts_fit_dev(Xu, xobs_diag, n, d, k, f);
+        fit_to_host(f, X, UZ, BBBH, nconst);
+        if (n2 == 0) return;
+        frk_plan* plan = new frk_plan();
+        try {
+            plan->mp = frk::plan_create_dev(f.Xu.p, n, d, f.BBBH.p, f.UZ.p, n + d + 1, k, f.nconst, f.shift, nullptr);
+            predict_host(plan, xnew, n2, X1, FRK_OUT_X1);
+        } catch (...) {
+            delete plan;
+            throw;
+        }
+        delete plan;
+    });
+}
+
+int32_t frk_getASCeigens(const double* A, int32_t n, double* value, double* vector) {
+    return guarded([&] {
+        if (n < 1) frk::fail(FRK_EINVAL, "A must be a non-empty square matrix");
+        require_device();
+        frk::DevBuf<double> dA(size_t(n) * n), dW(static_cast<size_t>(n));
+        FRK_CUDA(cudaMemcpy(dA.p, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+        frk::sym_eigen_dev(dA.p, n, dW.p);
+        FRK_CUDA(cudaMemcpy(value, dW.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        FRK_CUDA(cudaMemcpy(vector, dA.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -1,0 +1,315 @@
+// C ABI, part 2: fixed-rank-kriging reductions (K4, K5) and the fused predict -> reduce paths.
+#include "capi_internal.cuh"
+
+using frk_capi::guarded;
+using frk_capi::require_device;
+
+namespace frk_capi {
+frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, const double* UZ, int64_t uz_rows,
+                    int64_t uz_cols, const double* nconst, int32_t k, bool on_device);
+}
+
+namespace {
+
+#define FRK_CUBLAS(expr)                                                                       \
+    do {                                                                                       \
+        cublasStatus_t _s = (expr);                                                            \
+        if (_s != CUBLAS_STATUS_SUCCESS) ::frk::fail(3, "cuBLAS error %d at %s:%d", int(_s), __FILE__, __LINE__); \
+    } while (0)
+
+__global__ void axpy_kernel(double* __restrict__ acc, const double* __restrict__ x, int64_t len, int first) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < len) acc[i] = first ? x[i] : acc[i] + x[i];
+}
+
+// se[i] = sqrt(max(0, sum_j FV[i,j] * F[i,j]))     R/autoFRK.R:1220
+__global__ void rowdot_sqrt_kernel(const double* __restrict__ FV, const double* __restrict__ F, int64_t rows,
+                                   int64_t ld, int K, double* __restrict__ se) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= rows) return;
+    double s = 0.0;
+    for (int j = 0; j < K; ++j) s = fma(FV[i + int64_t(j) * ld], F[i + int64_t(j) * ld], s);
+    se[i] = sqrt(fmax(0.0, s));
+}
+
+int64_t default_chunk_rows(const frk::MrtsPlan* mp, int K) {
+    const int64_t bm = mp->ki ? mp->ki->bm : 128;
+    const int64_t wave = bm * mp->sm_count;
+    int64_t rc = (int64_t(2) << 30) / (int64_t(K) * 8);  // ~2 GB of basis per chunk
+    return std::max<int64_t>(wave, rc / wave * wave);
+}
+
+void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, const double* dZ, int T, int64_t ldz,
+                  double* dpacked, int64_t chunk_rows, cudaStream_t st) {
+    frk::MrtsPlan* mp = plan->mp;
+    const int K = mp->k;
+    if (chunk_rows <= 0) chunk_rows = default_chunk_rows(mp, K);
+    chunk_rows = std::min(chunk_rows, n2);
+    if (chunk_rows % 2) ++chunk_rows;  // keeps every chunk 16-byte aligned for the Gram kernel's cp.async path
+    if (plan->fchunk.n < size_t(chunk_rows) * K) plan->fchunk.alloc(size_t(chunk_rows) * K);
+    const size_t plen = frk::gram_packed_len(K, T);
+    if (plan->packed_tmp.n < plen) plan->packed_tmp.alloc(plen);
+    frk::GramWorkspace& ws = frk_capi::gram_workspace();
+    int first = 1;
+    for (int64_t r0 = 0; r0 < n2; r0 += chunk_rows) {
+        const int64_t rows = std::min(chunk_rows, n2 - r0);
+        frk::plan_predict_basis_dev(mp, dx + r0, rows, ldx, plan->fchunk.p, chunk_rows, st);
+        frk::gram_stats_dev(plan->fchunk.p, rows, K, chunk_rows, T > 0 ? dZ + r0 : nullptr, T, ldz, plan->packed_tmp.p, ws,
+                            st);
+        axpy_kernel<<<unsigned((plen + 255) / 256), 256, 0, st>>>(dpacked, plan->packed_tmp.p, int64_t(plen), first);
+        FRK_CUDA(cudaGetLastError());
+        mp->launches += 4;
+        first = 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t frk_gram_packed_len(int32_t K, int32_t T) { return int64_t(frk::gram_packed_len(K, T)); }
+
+int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
+                           int64_t ldz, double* d_packed, void* stream) {
+    return guarded([&] {
+        frk::gram_stats_dev(d_F, n, K, ldf, d_Z, T, ldz, d_packed, frk_capi::gram_workspace(),
+                            static_cast<cudaStream_t>(stream));
+    });
+}
+
+int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, double* G, double* C,
+                       double* zz) {
+    return guarded([&] {
+        require_device();
+        if (K < 1 || n < 1) frk::fail(FRK_EINVAL, "F must be a non-empty matrix");
+        if (T < 0) frk::fail(FRK_EINVAL, "T must be non-negative");
+        // stream the rows through the device in chunks (two buffers: H2D of chunk c+1 overlaps the Gram of chunk c)
+        int64_t rc = (int64_t(1) << 30) / (int64_t(K + T) * 8);
+        rc = std::max<int64_t>(4096, rc / 16 * 16);
+        rc = std::min(rc, (n + 1) / 2 * 2);
+        frk::DevBuf<double> dF[2], dZ[2], packed(frk::gram_packed_len(K, T)), ptmp(frk::gram_packed_len(K, T));
+        for (int b = 0; b < 2; ++b) {
+            dF[b].alloc(size_t(rc) * K);
+            if (T > 0) dZ[b].alloc(size_t(rc) * T);
+        }
+        cudaStream_t s_comp, s_copy;
+        FRK_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        FRK_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        cudaEvent_t ev_in[2], ev_done[2];
+        for (int b = 0; b < 2; ++b) {
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+        }
+        frk::GramWorkspace& ws = frk_capi::gram_workspace();
+        const size_t plen = frk::gram_packed_len(K, T);
+        try {
+            int c = 0, first = 1;
+            for (int64_t r0 = 0; r0 < n; r0 += rc, ++c) {
+                const int b = c & 1;
+                const int64_t rows = std::min(rc, n - r0);
+                if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
+                FRK_CUDA(cudaMemcpy2DAsync(dF[b].p, sizeof(double) * rc, F + r0, sizeof(double) * n, sizeof(double) * rows,
+                                           size_t(K), cudaMemcpyHostToDevice, s_copy));
+                if (T > 0)
+                    FRK_CUDA(cudaMemcpy2DAsync(dZ[b].p, sizeof(double) * rc, Z + r0, sizeof(double) * n,
+                                               sizeof(double) * rows, size_t(T), cudaMemcpyHostToDevice, s_copy));
+                FRK_CUDA(cudaEventRecord(ev_in[b], s_copy));
+                FRK_CUDA(cudaStreamWaitEvent(s_comp, ev_in[b], 0));
+                frk::gram_stats_dev(dF[b].p, rows, K, rc, T > 0 ? dZ[b].p : nullptr, T, rc, ptmp.p, ws, s_comp);
+                axpy_kernel<<<unsigned((plen + 255) / 256), 256, 0, s_comp>>>(packed.p, ptmp.p, int64_t(plen), first);
+                FRK_CUDA(cudaGetLastError());
+                FRK_CUDA(cudaEventRecord(ev_done[b], s_comp));
+                first = 0;
+            }
+            FRK_CUDA(cudaStreamSynchronize(s_comp));
+            FRK_CUDA(cudaMemcpy(G, packed.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+            if (T > 0 && C) FRK_CUDA(cudaMemcpy(C, packed.p + size_t(K) * K, sizeof(double) * K * T, cudaMemcpyDeviceToHost));
+            if (zz) FRK_CUDA(cudaMemcpy(zz, packed.p + size_t(K) * K + size_t(K) * T, sizeof(double), cudaMemcpyDeviceToHost));
+        } catch (...) {
+            cudaStreamDestroy(s_comp);
+            cudaStreamDestroy(s_copy);
+            for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_done[b]); }
+            throw;
+        }
+        cudaStreamDestroy(s_comp);
+        cudaStreamDestroy(s_copy);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_done[b]); }
+    });
+}
+
+int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, const double* d_Z,
+                                  int32_t T, int64_t ldz, double* d_packed, int64_t chunk_rows, void* stream) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        if (n2 < 1) frk::fail(FRK_EINVAL, "xnew must have at least one row");
+        if (ldx < n2 || (T > 0 && ldz < n2)) frk::fail(FRK_EINVAL, "leading dimensions must be >= n2");
+        predict_gram(plan, d_xnew, n2, ldx, d_Z, T, ldz, d_packed, chunk_rows, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int32_t frk_getHalf(const double* G, int64_t ldg, int32_t K, double* half) {
+    return guarded([&] {
+        require_device();
+        if (K < 1 || ldg < K) frk::fail(FRK_EINVAL, "G must be K x K with ldg >= K");
+        frk::DevBuf<double> dG(size_t(K) * K), dh(size_t(K) * K);
+        FRK_CUDA(cudaMemcpy2D(dG.p, sizeof(double) * K, G, sizeof(double) * ldg, sizeof(double) * K, size_t(K),
+                              cudaMemcpyHostToDevice));
+        frk::half_from_gram_dev(dG.p, K, K, dh.p);
+        FRK_CUDA(cudaMemcpy(half, dh.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t frk_cMLEimat_stats(const double* G, int64_t ldg, const double* C, int64_t ldc, double zz, int32_t K, int32_t T,
+                           int64_t n, double s, int32_t wsave, int32_t only_loglik, int32_t on_device, double* v,
+                           double* negloglik, double* M, double* w, double* V) {
+    return guarded([&] {
+        require_device();
+        if (K < 1 || T < 1) frk::fail(FRK_EINVAL, "K and T must be positive");
+        if (ldg < K || ldc < K) frk::fail(FRK_EINVAL, "leading dimensions must be >= K");
+        frk::DevBuf<double> dG, dC;
+        const double *pG = G, *pC = C;
+        int64_t lg = ldg, lc = ldc;
+        if (!on_device) {
+            dG.alloc(size_t(K) * K);
+            dC.alloc(size_t(K) * T);
+            FRK_CUDA(cudaMemcpy2D(dG.p, sizeof(double) * K, G, sizeof(double) * ldg, sizeof(double) * K, size_t(K),
+                                  cudaMemcpyHostToDevice));
+            FRK_CUDA(cudaMemcpy2D(dC.p, sizeof(double) * K, C, sizeof(double) * ldc, sizeof(double) * K, size_t(T),
+                                  cudaMemcpyHostToDevice));
+            pG = dG.p; pC = dC.p; lg = K; lc = K;
+        }
+        frk::CmleOut out;
+        frk::cmle_imat_from_stats_dev(pG, lg, pC, lc, zz, K, T, double(n), s, wsave != 0, only_loglik != 0, out);
+        if (v) *v = out.v;
+        if (negloglik) *negloglik = out.negloglik;
+        if (!only_loglik && M) FRK_CUDA(cudaMemcpy(M, out.M.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+        if (!only_loglik && wsave) {
+            if (w) FRK_CUDA(cudaMemcpy(w, out.w.p, sizeof(double) * K * T, cudaMemcpyDeviceToHost));
+            if (V) FRK_CUDA(cudaMemcpy(V, out.V.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+        }
+    });
+}
+
+int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS, const double* half, const double* JSJ,
+                 double s, double ldet, int32_t wsave, int32_t only_loglik, int32_t has_vfixed, double vfixed, double* v,
+                 double* negloglik, double* M, double* L, int32_t* nL) {
+    return guarded([&] {
+        require_device();
+        if (K < 1) frk::fail(FRK_EINVAL, "K must be positive");
+        frk::DevBuf<double> dh(size_t(K) * K), dJ(size_t(K) * K);
+        FRK_CUDA(cudaMemcpy(dh.p, half, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemcpy(dJ.p, JSJ, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        frk::CmleOut out;
+        frk::cmle_core_dev(dh.p, dJ.p, nullptr, K, K, TT, double(n), trS, s, ldet, wsave != 0, only_loglik != 0,
+                           has_vfixed != 0, vfixed, out);
+        if (v) *v = out.v;
+        if (negloglik) *negloglik = out.negloglik;
+        if (only_loglik) return;
+        if (M) FRK_CUDA(cudaMemcpy(M, out.M.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+        if (nL) *nL = wsave ? out.nL : 0;
+        if (wsave && Fk && L) {
+            // L = Fk %*% LA[, 1:nL]   (R/autoFRK.R:387-391), a plain library GEMM streamed over row chunks
+            frk::LinalgHandles& lh = frk::linalg_handles();
+            FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
+            const int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
+            frk::DevBuf<double> dF(size_t(rc) * K), dL(size_t(rc) * out.nL);
+            const double one = 1.0, zero = 0.0;
+            for (int64_t r0 = 0; r0 < n; r0 += rc) {
+                const int64_t rows = std::min(rc, n - r0);
+                FRK_CUDA(cudaMemcpy2D(dF.p, sizeof(double) * rc, Fk + r0, sizeof(double) * n, sizeof(double) * rows,
+                                      size_t(K), cudaMemcpyHostToDevice));
+                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), out.nL, K, &one, dF.p, int(rc),
+                                       out.LA.p, K, &zero, dL.p, int(rc)));
+                FRK_CUDA(cudaMemcpy2D(L + r0, sizeof(double) * n, dL.p, sizeof(double) * rc, sizeof(double) * rows,
+                                      size_t(out.nL), cudaMemcpyDeviceToHost));
+            }
+        }
+    });
+}
+
+int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, const double* w, int32_t T, const double* V,
+                             double* yhat, double* se) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        if (n2 <= 0) return;
+        frk::MrtsPlan* mp = plan->mp;
+        const int K = mp->k, d = mp->d;
+        if (T < 1 || !w || !yhat) frk::fail(FRK_EINVAL, "w (K x T) and yhat (n2 x T) are required");
+        frk::LinalgHandles& lh = frk::linalg_handles();
+        cudaStream_t st = nullptr;
+        FRK_CUBLAS(cublasSetStream(lh.blas, st));
+        int64_t rc = std::min<int64_t>(n2, default_chunk_rows(mp, K) / 2);
+        frk::DevBuf<double> dx(size_t(n2) * d), dw(size_t(K) * T), dV, dy(size_t(rc) * T), dFV, dse;
+        if (plan->fchunk.n < size_t(rc) * K) plan->fchunk.alloc(size_t(rc) * K);
+        FRK_CUDA(cudaMemcpy(dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemcpy(dw.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice));
+        const bool want_se = (V != nullptr && se != nullptr);
+        if (want_se) {
+            dV.alloc(size_t(K) * K);
+            dFV.alloc(size_t(rc) * K);
+            dse.alloc(static_cast<size_t>(rc));
+            FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        }
+        const double one = 1.0, zero = 0.0;
+        for (int64_t r0 = 0; r0 < n2; r0 += rc) {
+            const int64_t rows = std::min(rc, n2 - r0);
+            frk::plan_predict_basis_dev(mp, dx.p + r0, rows, n2, plan->fchunk.p, rc, st);
+            // yhat = basis %*% w                                          R/autoFRK.R:1216
+            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), T, K, &one, plan->fchunk.p, int(rc), dw.p, K,
+                                   &zero, dy.p, int(rc)));
+            FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n2, dy.p, sizeof(double) * rc, sizeof(double) * rows,
+                                       size_t(T), cudaMemcpyDeviceToHost, st));
+            if (want_se) {
+                // se = sqrt(pmax(0, rowSums((basis %*% V) * basis)))       R/autoFRK.R:1220
+                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), K, K, &one, plan->fchunk.p, int(rc), dV.p,
+                                       K, &zero, dFV.p, int(rc)));
+                rowdot_sqrt_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dFV.p, plan->fchunk.p, rows, rc, K, dse.p);
+                FRK_CUDA(cudaGetLastError());
+                FRK_CUDA(cudaMemcpyAsync(se + r0, dse.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+            }
+            FRK_CUDA(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,
+                              double* yhat, double* se) {
+    return guarded([&] {
+        require_device();
+        if (n <= 0) return;
+        if (K < 1 || T < 1 || !F || !w || !yhat) frk::fail(FRK_EINVAL, "F (n x K), w (K x T) and yhat (n x T) are required");
+        frk::LinalgHandles& lh = frk::linalg_handles();
+        cudaStream_t st = nullptr;
+        FRK_CUBLAS(cublasSetStream(lh.blas, st));
+        const int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
+        const bool want_se = (V != nullptr && se != nullptr);
+        frk::DevBuf<double> dF(size_t(rc) * K), dw(size_t(K) * T), dy(size_t(rc) * T), dV, dFV, dse;
+        FRK_CUDA(cudaMemcpy(dw.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice));
+        if (want_se) {
+            dV.alloc(size_t(K) * K);
+            dFV.alloc(size_t(rc) * K);
+            dse.alloc(static_cast<size_t>(rc));
+            FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        }
+        const double one = 1.0, zero = 0.0;
+        for (int64_t r0 = 0; r0 < n; r0 += rc) {
+            const int64_t rows = std::min(rc, n - r0);
+            FRK_CUDA(cudaMemcpy2DAsync(dF.p, sizeof(double) * rc, F + r0, sizeof(double) * n, sizeof(double) * rows,
+                                       size_t(K), cudaMemcpyHostToDevice, st));
+            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), T, K, &one, dF.p, int(rc), dw.p, K, &zero,
+                                   dy.p, int(rc)));                        // R/autoFRK.R:1216
+            FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n, dy.p, sizeof(double) * rc, sizeof(double) * rows,
+                                       size_t(T), cudaMemcpyDeviceToHost, st));
+            if (want_se) {                                                  // R/autoFRK.R:1220
+                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), K, K, &one, dF.p, int(rc), dV.p, K,
+                                       &zero, dFV.p, int(rc)));
+                rowdot_sqrt_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dFV.p, dF.p, rows, rc, K, dse.p);
+                FRK_CUDA(cudaGetLastError());
+                FRK_CUDA(cudaMemcpyAsync(se + r0, dse.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+            }
+            FRK_CUDA(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+}  // extern "C"

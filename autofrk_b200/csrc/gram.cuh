@@ -1,0 +1,21 @@
+// K4: Gram / cross-product / sum-of-squares reductions (see gram.cu).
+#pragma once
+#include "frk_common.cuh"
+
+namespace frk {
+
+struct GramWorkspace {
+    DevBuf<double> partial;  // row-split partial tiles
+    DevBuf<double> zzpart;   // per-block partial sums of squares
+    int64_t launches = 0;
+    int last_nsplit = 0, last_npairs = 0;
+};
+
+// number of doubles in the packed result [G (K x K, column-major, full symmetric) | C (K x T) | zz]
+size_t gram_packed_len(int K, int T);
+
+// dF n x K (ld ldf), dZ n x T (ld ldz; T may be 0) on the device -> dpacked on the device; asynchronous on st.
+void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
+                    double* dpacked, GramWorkspace& ws, cudaStream_t st);
+
+}  // namespace frk

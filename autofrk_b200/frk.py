@@ -1,0 +1,254 @@
+"""Host-side mirror of autoFRK's fixed-rank-kriging fit / predict interface on top of the C ABI.
+
+Same names and argument meaning as the reference's R functions; every n-sized product runs on the
+device (K4 Gram reductions, K1 basis evaluation) and every K x K eigen-stage in K5:
+  gram_stats        new: G = F'F, C = F'Z, zz  (R/helper.R:20, R/autoFRK.R:431-435)
+  getASCeigens      src/autoFRK.cpp:24-32        getEigen / getHalf   R/helper.R:12-26
+  cMLE              R/autoFRK.R:333-397          cMLEimat             R/autoFRK.R:399-480
+  selectBasis       R/autoFRK.R:199-331          indeMLE              R/autoFRK.R:739-843
+  autoFRK           R/autoFRK.R:121-197          predict_FRK          R/autoFRK.R:1168-1423
+Branches that belong to components SURVEY.md marks out of scope (sparse/non-identity D -> cMLEsp,
+LatticeKrig fine scale -> cMLElk, missing data -> EM0miss / kNN imputation) raise NotImplementedError
+naming the component; nothing silently falls back to host arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, fmat, lib, ptr
+from .mrts import MrtsBasis, getASCeigens, mrts, predict_mrts
+
+
+def gram_stats(Fk, Data=None):
+    """(G, C, zz) = (F'F, F'Z, sum(Z^2)) in one device pass over the rows."""
+    F = fmat(Fk, "Fk")
+    n, K = F.shape
+    Z = None if Data is None else fmat(Data, "Data")
+    T = 0 if Z is None else Z.shape[1]
+    if Z is not None and Z.shape[0] != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "Data must have as many rows as Fk")
+    G = np.empty((K, K), order="F")
+    Cm = np.empty((K, max(T, 1)), order="F")
+    zz = C.c_double(0.0)
+    check(lib.frk_gram_stats(ptr(F), n, K, None if Z is None else ptr(Z), T, ptr(G), ptr(Cm), C.byref(zz)))
+    return G, (Cm if T else None), zz.value
+
+
+def getEigen(A):
+    """R/helper.R:12-17."""
+    obj = getASCeigens(A)
+    return {"value": obj["value"][::-1].copy(), "vector": np.asfortranarray(obj["vector"][:, ::-1])}
+
+
+def getHalf(Fk, iDFk):
+    """R/helper.R:19-26: (t(Fk) %*% iDFk)^(-1/2)."""
+    F = fmat(Fk, "Fk")
+    if iDFk is Fk or (np.shape(iDFk) == F.shape and np.shares_memory(np.asarray(iDFk), np.asarray(Fk))):
+        G, _, _ = gram_stats(F)
+    else:
+        _, G, _ = gram_stats(F, iDFk)       # the K x K cross-product t(Fk) %*% iDFk   (R/helper.R:20)
+    return half_from_gram(G)
+
+
+def half_from_gram(G):
+    G = fmat(G, "G")
+    K = G.shape[0]
+    half = np.empty((K, K), order="F")
+    check(lib.frk_getHalf(ptr(G), K, K, ptr(half)))
+    return half
+
+
+def cmle_from_stats(G, Cm, zz, n, TT, s=0.0, wSave=False, onlylogLike=None, K=None, on_device=False):
+    """cMLEimat (R/autoFRK.R:399-480) from the sufficient statistics; K selects the leading K x K / K x T blocks."""
+    if onlylogLike is None:
+        onlylogLike = not wSave
+    if on_device:
+        Kfull = int(G.shape[0])
+        K = Kfull if K is None else int(K)
+        pG, pC, ldg, ldc = C.c_void_p(G.data_ptr()), C.c_void_p(Cm.data_ptr()), Kfull, Kfull
+    else:
+        G, Cm = fmat(G, "G"), fmat(Cm, "C")
+        Kfull = G.shape[0]
+        K = Kfull if K is None else int(K)
+        pG, pC, ldg, ldc = ptr(G), ptr(Cm), Kfull, Kfull
+    v, nll = C.c_double(0.0), C.c_double(0.0)
+    M = np.empty((K, K), order="F") if not onlylogLike else None
+    w = np.empty((K, TT), order="F") if (wSave and not onlylogLike) else None
+    V = np.empty((K, K), order="F") if (wSave and not onlylogLike) else None
+    check(lib.frk_cMLEimat_stats(pG, ldg, pC, ldc, float(zz), K, int(TT), int(n), float(s), int(bool(wSave)),
+                                 int(bool(onlylogLike)), int(bool(on_device)), C.byref(v), C.byref(nll),
+                                 None if M is None else ptr(M), None if w is None else ptr(w),
+                                 None if V is None else ptr(V)))
+    if onlylogLike:
+        return {"negloglik": nll.value}
+    out = {"v": v.value, "M": M, "s": s, "negloglik": nll.value}
+    if wSave:
+        out["w"], out["V"] = w, V
+    return out
+
+
+def cMLEimat(Fk, Data, s, wSave=False, S=None, onlylogLike=None):
+    """R/autoFRK.R:399-480."""
+    if S is not None:
+        raise NotImplementedError("cMLEimat(S=...) (precomputed covariance) has no caller in autoFRK")
+    F = fmat(Fk, "Fk")
+    Z = fmat(Data, "Data")
+    G, Cm, zz = gram_stats(F, Z)
+    return cmle_from_stats(G, Cm, zz, F.shape[0], Z.shape[1], s=s, wSave=wSave, onlylogLike=onlylogLike)
+
+
+def cMLE(Fk, TT, trS, half, JSJ=None, s=0.0, ldet=None, wSave=False, onlylogLike=None, vfixed=None):
+    """R/autoFRK.R:333-397."""
+    if onlylogLike is None:
+        onlylogLike = not wSave
+    F = fmat(Fk, "Fk")
+    n, K = F.shape
+    half, JSJ = fmat(half, "half"), fmat(JSJ, "JSJ")
+    v, nll, nL = C.c_double(0.0), C.c_double(0.0), C.c_int32(0)
+    M = np.empty((K, K), order="F")
+    L = np.empty((n, K), order="F") if (wSave and not onlylogLike) else None
+    check(lib.frk_cMLE(ptr(F), n, K, int(TT), float(trS), ptr(half), ptr(JSJ), float(s),
+                       0.0 if ldet is None else float(ldet), int(bool(wSave)), int(bool(onlylogLike)),
+                       int(vfixed is not None), 0.0 if vfixed is None else float(vfixed), C.byref(v), C.byref(nll),
+                       ptr(M), None if L is None else ptr(L), C.byref(nL)))
+    if onlylogLike:
+        return {"negloglik": nll.value}
+    return {"v": v.value, "M": M, "s": s, "negloglik": nll.value, "L": None if L is None else L[:, :nL.value]}
+
+
+def kgrid(d, maxK):
+    """Default K sequence, R/autoFRK.R:254-257."""
+    K = np.unique(np.round(np.arange(d + 1, maxK + 1e-9, maxK ** (1.0 / 3) * d))).astype(int)
+    if K.size > 30:
+        K = np.unique(np.round(np.linspace(d + 1, maxK, 30))).astype(int)
+    return K
+
+
+def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, method="fast", n_neighbor=3,
+                maxknot=5000, DfromLK=None, Fk=None):
+    """R/autoFRK.R:199-331 (identity D, complete data, method = "fast").
+
+    The AIC sweep uses ONE max-K pass over the rows: every candidate K works on the leading K columns of
+    Fk, i.e. on the leading principal blocks of G = F'F and C = F'Z (R recomputes both for each K)."""
+    if D is not None or DfromLK is not None:
+        raise NotImplementedError("non-identity D / LatticeKrig (cMLEsp, cMLElk) is out of scope (SURVEY.md 2 #19-20)")
+    if method != "fast":
+        raise NotImplementedError('method="EM" (EM0miss) is out of scope (SURVEY.md 2 #21)')
+    Z = fmat(Data, "Data")
+    if np.isnan(Z).any():
+        raise NotImplementedError("missing values need kNN imputation / EM0miss, out of scope (SURVEY.md 2 #21, #25)")
+    loc = fmat(loc, "loc")
+    d = loc.shape[1]
+    N = Z.shape[0]
+    klim = int(min(N, np.round(10 * math.sqrt(N))))             # :222
+    if N < maxknot:
+        knot = loc                                              # :223-224
+    else:
+        raise NotImplementedError("N >= maxknot needs subKnot (R RNG), out of scope: pass G = mrts(knot, K, loc)")
+    if maxK is not None:
+        maxK = int(np.round(maxK))
+    elif Kseq is not None:
+        maxK = int(np.round(max(Kseq)))
+    else:
+        maxK = klim                                             # :228-236
+    if Kseq is not None:
+        K = np.array(sorted(set(int(np.round(k)) for k in Kseq)))
+        if K.max() > maxK:
+            raise ValueError("maximum of Kseq is larger than maxK!")
+        K = K[K > d]
+        if K.size == 0:
+            raise ValueError("Not valid Kseq!")
+    else:
+        K = kgrid(d, maxK)                                      # :254-257
+    if Fk is None:
+        Fk = mrts(knot, int(K.max()), loc, maxknot)             # :260
+    TT = Z.shape[1]
+    G, Cm, zz = gram_stats(Fk.X, Z)                             # one pass; trS = zz/TT (:304)
+    AIC = np.full(K.size, np.inf)
+    for i, k in enumerate(K):                                   # :305-317
+        AIC[i] = cmle_from_stats(G, Cm, zz, N, TT, s=0.0, wSave=False, onlylogLike=True, K=int(k))["negloglik"]
+    df = np.where(K <= TT, K * (K + 1) / 2 + 1, K * TT + 1 - TT * (TT - 1) / 2)   # :321
+    AIC = AIC + 2 * df                                          # :322
+    Kopt = int(K[np.argmin(AIC)])                               # :323
+    out = Fk.leading(Kopt)                                      # :324-328
+    out.AIC, out.Kgrid = AIC, K
+    return out
+
+
+def indeMLE(Data, Fk, D=None, maxit=50, avgtol=1e-6, wSave=False, DfromLK=None, vfixed=None, sigma_FRK=None):
+    """R/autoFRK.R:739-843, the isimat / complete-data branch (:778-803)."""
+    if D is not None or DfromLK is not None:
+        raise NotImplementedError("non-identity D / LatticeKrig (cMLEsp, cMLElk) is out of scope (SURVEY.md 2 #19-20)")
+    Z = fmat(Data, "Data")
+    if np.isnan(Z).any():
+        raise NotImplementedError("missing values (EM0miss) are out of scope (SURVEY.md 2 #21)")
+    F = Fk.X if isinstance(Fk, MrtsBasis) else fmat(Fk, "Fk")
+    sigma = 0.0 if sigma_FRK is None else float(sigma_FRK)      # options(sigma_FRK) :779-783
+    out = cMLEimat(F, Z, s=sigma, wSave=wSave)                  # :787
+    if "v" in out:                                              # :788-795
+        out["s"] = out["v"] if sigma == 0 else sigma
+        del out["v"]
+    if wSave:
+        out["pinfo"] = {"pick": np.arange(Z.shape[0])}          # :800 (D0 = identity)
+    return out
+
+
+def autoFRK(Data, loc, mu=0.0, D=None, G=None, finescale=False, maxit=50, tolerance=1e-6, maxK=None, Kseq=None,
+            method="fast", n_neighbor=3, maxknot=5000):
+    """R/autoFRK.R:121-197 (finescale = FALSE)."""
+    if finescale:
+        raise NotImplementedError("finescale=TRUE (LatticeKrig) is out of scope (SURVEY.md 2 #20)")
+    Z = fmat(Data, "Data") - mu                                 # :125
+    if G is not None:
+        Fk = G                                                  # :126-127
+    else:
+        Fk = selectBasis(Z, loc, D, maxit, tolerance, maxK, Kseq, method, n_neighbor, maxknot, None)  # :129-132
+    obj = indeMLE(Z, Fk, D, maxit, avgtol=tolerance, wSave=True)  # :151
+    obj["G"] = Fk                                               # :185
+    obj["LKobj"] = None
+    return obj
+
+
+def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=None, mu_new=0.0, se_report=False):
+    """R/autoFRK.R:1168-1423, LKobj = NULL and obsData = NULL: yhat = basis %*% w (:1216),
+    se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (:1220), both fused behind the basis evaluation."""
+    if "w" not in obj:
+        raise ValueError('input model (object) should use the option "wsave=TRUE"!')   # :1171-1173
+    if obsData is not None:
+        raise NotImplementedError("predict.FRK(obsData=...) re-solves with invCz; next row of SURVEY.md 8(f)")
+    if newloc is None:
+        newloc = obsloc
+    G = obj["G"]
+    if basis is None and newloc is not None and not isinstance(G, MrtsBasis):
+        raise ValueError("Basis matrix of new locations should be given (unless the model was fitted with mrts bases)!")
+    w = fmat(obj["w"], "w")
+    K, TT = w.shape
+    V = fmat(obj["V"], "V") if se_report else None
+    se = None
+    if basis is None and newloc is not None:
+        # basis <- predict.mrts(object$G, newx = newloc) (:1184), fused with the two products on the device
+        x = fmat(newloc, "newloc")
+        kstar = G.X.shape[1] - G.Xu.shape[1] - 1
+        if kstar > 0:
+            n2 = x.shape[0]
+            yhat = np.empty((n2, TT), order="F")
+            se = np.empty(n2) if se_report else None
+            check(lib.frk_plan_predict_frk(G.plan()._h, ptr(x), n2, ptr(w), TT, None if V is None else ptr(V), ptr(yhat),
+                                           None if se is None else ptr(se)))
+            return {"pred.value": yhat + mu_new, "se": None if se is None else np.repeat(se[:, None], TT, axis=1)}
+        basis = predict_mrts(G, x)                              # polynomial-only basis (k* = 0)
+    B = fmat(G.X if isinstance(G, MrtsBasis) else G, "G") if basis is None else fmat(basis, "basis")   # :1176,1182
+    if newloc is not None and B.shape[0] != fmat(newloc).shape[0]:
+        raise ValueError("Dimensions of newloc and basis are not compatible!")          # :1203-1207
+    if B.shape[1] != K:
+        raise ValueError("Dimensions of basis and object$w are not compatible!")
+    n2 = B.shape[0]
+    yhat = np.empty((n2, TT), order="F")
+    se = np.empty(n2) if se_report else None
+    check(lib.frk_basis_predict_frk(ptr(B), n2, K, ptr(w), TT, None if V is None else ptr(V), ptr(yhat),
+                                    None if se is None else ptr(se)))
+    return {"pred.value": yhat + mu_new, "se": None if se is None else np.repeat(se[:, None], TT, axis=1)}

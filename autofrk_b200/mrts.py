@@ -175,3 +175,110 @@ def predict_mrts(obj: MrtsBasis, newx=None, use_plan=True):
     shift = Xu.mean(axis=0)                                     # :1462
     X2 = np.column_stack([np.ones(x0.shape[0]), (x0 - shift) / obj.nconst])  # :1463-1464
     return np.column_stack([X2, X1])                            # :1466
+
+
+def _check_xobs_diag(xobs_diag, d):
+    xd = fmat(xobs_diag, "xobs_diag")
+    return xd
+
+
+def mrtsrcpp(Xu, xobs_diag, k):
+    """Drop-in for R/RcppExports.R:8-10 (src/autoFRK.cpp:224-242): list(X, UZ, BBBH, nconst)."""
+    Xu = fmat(Xu, "Xu")
+    xd = _check_xobs_diag(xobs_diag, Xu.shape[1])
+    n, d = Xu.shape
+    k = int(k)
+    kk = max(k, 0)
+    X = np.empty((n, kk + d + 1), order="F")
+    UZ = np.empty((n + d + 1, kk + d + 1), order="F")
+    BBBH = np.empty((d + 1, n), order="F")
+    nconst = np.empty(d)
+    check(lib.frk_mrtsrcpp(ptr(Xu), n, d, ptr(xd), xd.shape[0], xd.shape[1], k, ptr(X), ptr(UZ), ptr(BBBH),
+                           ptr(nconst)))
+    return {"X": X, "UZ": UZ, "BBBH": BBBH, "nconst": nconst}
+
+
+def mrtsrcpp_predict0(Xu, xobs_diag, xnew, k):
+    """Drop-in for R/RcppExports.R:12-14 (src/autoFRK.cpp:248-281): fit + evaluate, list(X, UZ, BBBH, nconst, X1)."""
+    Xu, xnew = fmat(Xu, "Xu"), fmat(xnew, "xnew")
+    xd = _check_xobs_diag(xobs_diag, Xu.shape[1])
+    n, d = Xu.shape
+    n2 = xnew.shape[0]
+    k = int(k)
+    kk = max(k, 0)
+    X = np.empty((n, kk + d + 1), order="F")
+    UZ = np.empty((n + d + 1, kk + d + 1), order="F")
+    BBBH = np.empty((d + 1, n), order="F")
+    nconst = np.empty(d)
+    X1 = np.empty((n2, kk), order="F")
+    check(lib.frk_mrtsrcpp_predict0(ptr(Xu), n, d, ptr(xd), xd.shape[0], xd.shape[1], ptr(xnew), n2, xnew.shape[1], k,
+                                    ptr(X), ptr(UZ), ptr(BBBH), ptr(nconst), ptr(X1)))
+    return {"X": X, "UZ": UZ, "BBBH": BBBH, "nconst": nconst, "X1": X1}
+
+
+def getASCeigens(A):
+    """Drop-in for R/RcppExports.R:4-6 (src/autoFRK.cpp:24-32): list(value ascending, vector)."""
+    A = fmat(A, "A")
+    n = A.shape[0]
+    if A.shape[1] != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "A must be square")
+    value = np.empty(n)
+    vector = np.empty((n, n), order="F")
+    check(lib.frk_getASCeigens(ptr(A), n, ptr(value), ptr(vector)))
+    return {"value": value, "vector": vector}
+
+
+def unique_rows(x):
+    """R `unique` on a matrix (R/helper.R:245-247): first occurrences in original order."""
+    x = fmat(x)
+    _, idx = np.unique(x, axis=0, return_index=True)
+    return np.asfortranarray(x[np.sort(idx)])
+
+
+def mrts(knot, k, x=None, maxknot=5000):
+    """mrts() front-end, R/autoFRK.R:1050-1140.  Returns an MrtsBasis (the R `mrts` object)."""
+    xobs = fmat(knot, "knot")                                   # :1055-1059
+    Xu = unique_rows(xobs)                                      # :1060
+    if x is None and Xu.size != xobs.size:                      # :1061-1063
+        x = xobs
+    n, ndims = Xu.shape
+    if k < ndims + 1:
+        raise ValueError("k-1 can not be smaller than the number of dimensions!")   # :1067-1069
+    if maxknot < n:
+        # :1070-1079 calls subKnot (R/helper.R:93-161), which draws with R's RNG (set.seed + sample);
+        # knot thinning stays in R -- knots are an input of this library (SURVEY.md section 2, #24)
+        raise NotImplementedError("more than maxknot unique knots: thin them with autoFRK:::subKnot in R first")
+    xobs_diag = xobs_diag_of(xobs, n)                           # :1080
+    kstar = int(k) - ndims - 1
+    res = {}
+    if x is not None:
+        x = fmat(x, "x")                                        # :1082-1086
+        if kstar > 0:
+            res = mrtsrcpp_predict0(Xu, xobs_diag, x, kstar)    # :1088
+        else:                                                   # :1091-1096
+            X2 = Xu - Xu.mean(axis=0)
+            shift = Xu.mean(axis=0)
+            nconst = np.sqrt(np.diag(X2.T @ X2))
+            X2 = np.column_stack([np.ones(x.shape[0]), (x - shift) / nconst * np.sqrt(n)])
+            res = {"X": X2[:, :k]}
+            x = None
+    else:
+        if kstar > 0:
+            res = mrtsrcpp(Xu, xobs_diag, kstar)                # :1101
+        else:                                                   # :1103-1107
+            X2 = Xu - Xu.mean(axis=0)
+            shift = Xu.mean(axis=0)
+            nconst = np.sqrt(np.diag(X2.T @ X2))
+            X2 = np.column_stack([np.ones(n), (Xu - shift) / nconst * np.sqrt(n)])
+            res = {"X": X2[:, :k]}
+    nconst = res.get("nconst")
+    if nconst is None:                                          # :1111-1114 (undivided norm: quirk 5 of SURVEY 9)
+        X2 = Xu - Xu.mean(axis=0)
+        nconst = np.sqrt(np.diag(X2.T @ X2))
+    obj = MrtsBasis(res["X"], res.get("UZ"), Xu, nconst, res.get("BBBH"))   # :1115-1120
+    if x is None:
+        return obj                                              # :1121-1122
+    shift = Xu.mean(axis=0)                                     # :1124
+    X2 = np.column_stack([np.ones(x.shape[0]), (x - shift) / obj.nconst])   # :1125-1126
+    obj0 = np.column_stack([X2, res["X1"]]) if kstar > 0 else X2            # :1127-1131
+    return MrtsBasis(obj0, obj.UZ, Xu, obj.nconst, obj.BBBH)

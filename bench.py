@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- mrts basis evaluations per second (n * K, FP64) on N B200s of one node.
+
+A "step" is one pass of the hot path (fused TPS evaluation + projection + polynomial columns,
+`predict.mrts`) over one batch of synthetic locations.  Workload: the configuration BASELINE.json's
+metric is quoted on (configs[4]: 100M 2-D locations x 1,000 knots, K=500 on 8 GPUs), row-sharded,
+i.e. 12.5M locations per GPU (weak scaling: N GPUs evaluate N x 12.5M locations).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework
+  python bench.py --impl reference ...                           # the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(d=2, knots=1000, K=500, rows_per_gpu=12_500_000)
+METRIC = "mrts_basis_evals_per_sec"
+UNIT = "basis_evals/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic problem (identical on every rank: knots seed 7; locations seed 1234 + rank)
+# ----------------------------------------------------------------------------------------------
+def make_knots(m, d):
+    return np.random.default_rng(7).random((m, d))
+
+
+def clock_sampler(stop, samples, index):
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            samples.append((sm, mx, rs, pw))
+            time.sleep(0.05)
+    except Exception as e:  # pragma: no cover
+        samples.append(("error", str(e)))
+
+
+def summarize_clocks(samples):
+    good = [s for s in samples if s and s[0] != "error"]
+    if not good:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+    bits = 0
+    for s in good:
+        bits |= int(s[2])
+    reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
+    return {"sm_mhz": float(np.median([s[0] for s in good])), "sm_max_mhz": float(good[0][1]),
+            "power_w_max": float(max(s[3] for s in good)), "samples": len(good), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_predict_rows(Xu, UZ, BBBH, nconst, xnew, K, threads):
+    """predict.mrts on the CPU the way the reference does it: scalar C loop for the kernel matrix
+    (src/autoFRK.cpp:109-153, one row block per host thread), BLAS GEMM for the projection (:316-324)."""
+    import ctypes as C
+
+    from autofrk_b200 import build
+
+    lib = C.CDLL(str(build.build_oracle()))
+    lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                       C.c_int64]
+    n2_all, d = xnew.shape
+    m = Xu.shape[0]
+    kstar = K - d - 1
+    Xuf = np.asfortranarray(Xu)
+    W = UZ[:m, :K]                                    # predict.mrts passes k = K (R/autoFRK.R:1458)
+    Cpoly = BBBH @ W
+    shift = Xu.mean(axis=0)
+    out = np.empty((n2_all, K), order="F")
+    chunk = 100_000                                   # the reference does not chunk (it would need n2*m*8 bytes)
+    with ThreadPoolExecutor(threads) as ex:
+        for c0 in range(0, n2_all, chunk):
+            xc = np.asfortranarray(xnew[c0:c0 + chunk])
+            n2 = xc.shape[0]
+            H = np.empty((n2, m), order="F")
+            blocks = np.linspace(0, n2, threads + 1).astype(np.int64)
+
+            def work(i):
+                r0, r1 = int(blocks[i]), int(blocks[i + 1])
+                if r1 > r0:
+                    lib.oracle_tpm_predict(xc.ctypes.data + 8 * r0, r1 - r0, n2, Xuf.ctypes.data, m, d,
+                                           H.ctypes.data + 8 * r0, n2)
+
+            list(ex.map(work, range(threads)))
+            X1 = H @ W - np.column_stack([np.ones(n2), xc]) @ Cpoly
+            out[c0:c0 + n2, 0] = 1.0
+            out[c0:c0 + n2, 1:d + 1] = (xc - shift) / nconst
+            out[c0:c0 + n2, d + 1:] = X1[:, :kstar]
+    return out
+
+
+def oracle_fit(Xu, K):
+    import oracle as O
+    from oracle.mrts_oracle import xobs_diag_of
+
+    m, d = Xu.shape
+    return O.mrtsrcpp(Xu, xobs_diag_of(Xu, m), K - d - 1)
+
+
+def run_cpu(sample_rows, steps, warmup, threads):
+    w = WORKLOAD
+    Xu = make_knots(w["knots"], w["d"])
+    fit = oracle_fit(Xu, w["K"])
+    rng = np.random.default_rng(1234)
+    x = rng.random((sample_rows, w["d"]))
+    for _ in range(warmup):
+        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x[: max(1000, sample_rows // 10)], w["K"], threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x, w["K"], threads)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_rows * w["K"] / dt, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    rows = 400_000
+    val, dt = run_cpu(rows, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
+    w = WORKLOAD
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"predict.mrts: {w['rows_per_gpu']} 2-D locations/GPU x {w['knots']} knots, K={w['K']}",
+                   "sample": f"{rows} rows per step (the path is linear in rows)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{rows} rows x {w['knots']} knots x K={w['K']} per step; scalar C kernel loop "
+                                   f"(one row block per thread) + OpenBLAS GEMM"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def measure_dgemm_peak(torch, n=8192, reps=5):
+    a = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    b = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from autofrk_b200 import mrts as G
+    from autofrk_b200._lib import FRK_OUT_BASIS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (autofrk_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOAD
+    d, m, K = w["d"], w["knots"], w["K"]
+    kstar = K - d - 1
+    n2 = args.rows or w["rows_per_gpu"]
+
+    # fit: knots + eigenvector block.  The fit is replicated (identical on every rank).
+    Xu = make_knots(m, d)
+    fit = fit_for_bench(Xu, K)
+    basis = G.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    plan = basis.plan()
+
+    dgemm_peak = measure_dgemm_peak(torch) if rank == 0 else None
+
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=gen).T        # 200 MB > L2
+    out = torch.empty((K, n2), dtype=torch.float64, device="cuda").T                    # 50 GB
+
+    def step():
+        plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clock_sampler, args=(stop, samples, local), daemon=True)
+    th.start()
+    l0 = plan.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    stop.set()
+    th.join()
+    launches = plan.launches - l0
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    value = world * n2 * K / (ms_step * 1e-3)
+
+    # end to end through the host-buffer API (pinned host memory, H2D + D2H inside the timed region)
+    n2e = min(n2, args.e2e_rows)
+    xh = torch.empty((d, n2e), dtype=torch.float64).pin_memory()
+    xh.copy_(x.T[:, :n2e])
+    oh = torch.empty((K, n2e), dtype=torch.float64).pin_memory()
+    xh_np, oh_np = xh.numpy().T, oh.numpy().T                                          # column-major views
+    plan.predict(xh_np, mode=FRK_OUT_BASIS, out=oh_np)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        plan.predict(xh_np, mode=FRK_OUT_BASIS, out=oh_np)
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * n2e * K / float(dt.item())
+    # the two paths run the same kernel on the same rows
+    same = bool(torch.equal(torch.from_numpy(oh_np[:1000].copy()), out[:1000].cpu()))
+
+    if rank == 0:
+        flops = 2.0 * n2 * m * kstar                     # credited: projection only
+        achieved = flops / (ms_step * 1e-3) / 1e12
+        threads = os.cpu_count() or 1
+        cpu_rows = 2_000_000
+        cpu_val, cpu_dt = run_cpu(cpu_rows, 1, 1, threads)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"predict.mrts (fused TPS eval + projection + polynomial columns): {n2} 2-D locations/GPU "
+                            f"x {m} knots, K={K} (k*={kstar}); BASELINE configs[4] row-sharded over {world} GPU(s)",
+                "rows_per_gpu": n2, "knots": m, "K": K, "d": d,
+                "l2": "inputs (200 MB of coordinates) and outputs (50 GB) exceed the 126 MB L2; no flush needed",
+                "fit": fit.get("how", "device"),
+                "kernel": plan.info,
+            },
+            "roofline": {
+                "bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": achieved / dgemm_peak,
+                "peak_source": "FP64: cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json holds no FP64 peak)",
+                "flops_per_launch": flops, "traffic": None,
+                "kernel": "mrts_predict_kernel (DMMA.8x8x4)",
+            },
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{cpu_rows} rows of the same workload ({cpu_dt:.1f} s): scalar C kernel loop "
+                                       f"(src/autoFRK.cpp:109-153, one row block per thread) + OpenBLAS GEMM"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n2e * d * 8),
+                    "d2h_bytes_per_step": int(n2e * K * 8),
+                    "sample": f"{n2e} rows/GPU per step through frk_plan_predict (host buffers, pinned)",
+                    "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": summarize_clocks(samples),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def fit_for_bench(Xu, K):
+    """mrts fit of the knots.  Uses the device fit when the library provides it; the eigenvector
+    block is replicated, so computing it once per process is part of setup, not of the timed path."""
+    from autofrk_b200 import mrts as G
+
+    m, d = Xu.shape
+    if hasattr(G, "mrtsrcpp"):
+        r = G.mrtsrcpp(Xu, G.xobs_diag_of(Xu, m), K - d - 1)
+        r["how"] = "frk_mrtsrcpp on device"
+        return r
+    raise SystemExit("device fit unavailable")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's 12.5M)")
+    ap.add_argument("--e2e-rows", type=int, default=1_000_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

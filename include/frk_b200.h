@@ -55,6 +55,25 @@ int32_t frk_mrtsrcpp_predict(const double* Xu, int64_t n, int32_t d, const doubl
                              int64_t uz_cols, const double* nconst, int64_t nconst_len, int32_t k,
                              double* X1);
 
+/* replaces _autoFRK_mrtsrcpp (src/RcppExports.cpp:28-39 -> src/autoFRK.cpp:224-242): the mrts fit.
+ *   Xu n x d knots, xobs_diag xd_rows x xd_cols (must be d x d), k = number of eigen-columns (K - d - 1).
+ * Outputs (caller-allocated): X n x (k+d+1), UZ (n+d+1) x (k+d+1), BBBH (d+1) x n, nconst d.
+ * Eigenvector signs are arbitrary in the reference (Spectra); here every eigenvector is normalised so
+ * that its largest-magnitude entry is positive, which makes the fit reproducible across ranks. */
+int32_t frk_mrtsrcpp(const double* Xu, int64_t n, int32_t d, const double* xobs_diag, int32_t xd_rows,
+                     int32_t xd_cols, int32_t k, double* X, double* UZ, double* BBBH, double* nconst);
+
+/* replaces _autoFRK_mrtsrcpp_predict0 (src/RcppExports.cpp:41-53 -> src/autoFRK.cpp:248-281): fit, then
+ * evaluate at xnew (n2 x xnew_cols, must have d columns).  X1 is n2 x k.  The eigenvector block never
+ * leaves the device between the fit and the evaluation. */
+int32_t frk_mrtsrcpp_predict0(const double* Xu, int64_t n, int32_t d, const double* xobs_diag, int32_t xd_rows,
+                              int32_t xd_cols, const double* xnew, int64_t n2, int32_t xnew_cols, int32_t k,
+                              double* X, double* UZ, double* BBBH, double* nconst, double* X1);
+
+/* replaces _autoFRK_getASCeigens (src/RcppExports.cpp:17-26 -> src/autoFRK.cpp:24-32): full symmetric
+ * eigendecomposition of the n x n matrix A (lower triangle read), values ascending, vectors n x n. */
+int32_t frk_getASCeigens(const double* A, int32_t n, double* value, double* vector);
+
 /* ---------------------------------------------------------------------------------------------
  * Plans: keep knots / eigenvector block / polynomial correction resident on the device so that
  * repeated predict.mrts() calls (and the multi-GPU row shards) pay the upload and packing once.
@@ -78,6 +97,57 @@ int32_t frk_plan_predict(frk_plan* plan, const double* xnew, int64_t n2, double*
 /* device buffers: xnew n2 x d (ld ldx), out n2 x k (ld ldo); asynchronous on `stream` */
 int32_t frk_plan_predict_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, double* d_out,
                              int64_t ldo, int32_t out_mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fixed-rank-kriging reductions.  These are R code in the reference (base `%*%`, `eigen`); the
+ * R-side functions named below become thin wrappers around them.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Sufficient statistics of the fit in one pass over the rows:
+ *   G = F'F (K x K; replaces `t(Fk) %*% iDFk`, R/helper.R:20), C = F'Z (K x T; all that
+ *   R/autoFRK.R:433-435 needs because ihF %*% Data == half %*% (F'Z)), zz = sum(Z^2) (R/autoFRK.R:431).
+ * F is n x K, Z is n x T (T may be 0, then Z, C may be NULL), host pointers, column-major. */
+int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, double* G, double* C,
+                       double* zz);
+/* length of the packed device result [G (K*K) | C (K*T) | zz (1)] */
+int64_t frk_gram_packed_len(int32_t K, int32_t T);
+/* device pointers: F n x K (ld ldf), Z n x T (ld ldz) -> d_packed; asynchronous on `stream`.
+ * Multi-GPU: every rank calls this on its row shard, then one allreduce(sum) of d_packed. */
+int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
+                           int64_t ldz, double* d_packed, void* stream);
+/* fused predict.mrts -> Gram: the n2 x K basis is produced chunk by chunk (chunk_rows rows, 0 = default)
+ * and reduced at once, so it is never materialised.  d_Z is n2 x T (ld ldz). */
+int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, const double* d_Z,
+                                  int32_t T, int64_t ldz, double* d_packed, int64_t chunk_rows, void* stream);
+
+/* getHalf (R/helper.R:19-26) given G = t(Fk) %*% iDFk (K x K, ld ldg, lower triangle read): half = G^(-1/2),
+ * zero eigenvalues -> 0. */
+int32_t frk_getHalf(const double* G, int64_t ldg, int32_t K, double* half);
+
+/* cMLEimat (R/autoFRK.R:399-480) from the sufficient statistics.  G (ld ldg) and C (ld ldc) may be the
+ * leading K x K / K x T blocks of larger matrices (selectBasis' AIC sweep, R/autoFRK.R:305-317).
+ * `n` = nrow(Fk).  Outputs: v, negloglik always; M (K x K) unless only_loglik; w (K x T), V (K x K) if wsave.
+ * Unused outputs may be NULL.  `on_device` != 0: G and C are device pointers (outputs stay host pointers). */
+int32_t frk_cMLEimat_stats(const double* G, int64_t ldg, const double* C, int64_t ldc, double zz, int32_t K, int32_t T,
+                           int64_t n, double s, int32_t wsave, int32_t only_loglik, int32_t on_device, double* v,
+                           double* negloglik, double* M, double* w, double* V);
+
+/* cMLE (R/autoFRK.R:333-397): half, JSJ are K x K host matrices; Fk (n x K, host, may be NULL) is only needed
+ * for L (n x nL, written when wsave != 0 and Fk, L are non-NULL; L must hold n x K doubles). */
+int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS, const double* half, const double* JSJ,
+                 double s, double ldet, int32_t wsave, int32_t only_loglik, int32_t has_vfixed, double vfixed,
+                 double* v, double* negloglik, double* M, double* L, int32_t* nL);
+
+/* predict.FRK core (R/autoFRK.R:1216,1220) fused behind the basis evaluation: yhat = basis %*% w (n2 x T),
+ * se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (n2; V, se may be NULL).  Host pointers; the n2 x K
+ * basis never leaves the device. */
+int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, const double* w, int32_t T,
+                             const double* V, double* yhat, double* se);
+
+/* the same two products for a basis matrix the caller already holds (predict.FRK with `basis=` or with
+ * newloc = NULL, where R uses object$G): F is n x K, host, column-major; streamed through the device. */
+int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,
+                              double* yhat, double* se);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_symbols():
     text = (ROOT / "include" / "frk_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(frk_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(frk_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported():

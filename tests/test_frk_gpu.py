@@ -1,0 +1,206 @@
+"""K4/K5 parity on the GPU: Gram reductions, the K x K cMLE stage, autoFRK() and predict.FRK() vs the oracle."""
+import numpy as np
+import pytest
+
+from util import TOL, colrel, relmax
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, K, T, seed, rank=5):
+    rng = np.random.default_rng(seed)
+    F = rng.standard_normal((n, K))
+    F[:, 0] = 1.0
+    wts = np.zeros((K, T))
+    wts[:rank] = rng.standard_normal((rank, T)) * 3.0
+    Z = F @ wts + rng.standard_normal((n, T))
+    return F, Z
+
+
+@pytest.mark.parametrize("n,K,T", [(5000, 30, 3), (20011, 130, 5), (4096, 128, 128), (30000, 500, 100), (777, 257, 1),
+                                   (3000, 40, 0)])
+def test_gram_stats_matches_numpy(n, K, T):
+    from autofrk_b200 import frk as G
+
+    F, Z = _data(n, K, max(T, 1), seed=n + K)
+    if T == 0:
+        Gm, Cm, zz = G.gram_stats(F)
+        assert Cm is None and zz == 0.0
+    else:
+        Gm, Cm, zz = G.gram_stats(F, Z)
+        assert relmax(Cm, F.T @ Z) < 1e-12
+        assert abs(zz - np.sum(Z * Z)) / np.sum(Z * Z) < 1e-13
+    assert relmax(Gm, F.T @ F) < 1e-12
+    assert np.array_equal(Gm, Gm.T)          # exactly symmetric by construction
+
+
+def test_gram_dev_and_fused_predict_gram():
+    """device-pointer API (row shards + packed buffer) and the fused predict -> Gram path (F never materialised)."""
+    import ctypes as C
+    import torch
+    import oracle as O
+    from oracle.mrts_oracle import xobs_diag_of
+    from autofrk_b200 import _lib, mrts as GM
+
+    rng = np.random.default_rng(0)
+    d, m, K, T, n = 2, 300, 60, 4, 50_001
+    Xu = rng.random((m, d))
+    fit = O.mrtsrcpp(Xu, xobs_diag_of(Xu, m), K - d - 1)
+    obj = GM.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    plan = obj.plan()
+    x = torch.rand((d, n), dtype=torch.float64, device="cuda").T
+    Z = torch.randn((T, n), dtype=torch.float64, device="cuda").T
+    F = plan.predict_dev(x, mode=_lib.FRK_OUT_BASIS)
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    assert plen == K * K + K * T + 1
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # (1) materialised F, two row shards reduced like the multi-GPU path (sum of packed buffers)
+    packed = torch.zeros(plen, dtype=torch.float64, device="cuda")
+    for r0, r1 in ((0, 20_000), (20_000, n)):
+        part = torch.empty(plen, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F[r0:].data_ptr()), r1 - r0, K, n, C.c_void_p(Z[r0:].data_ptr()),
+                                               T, n, C.c_void_p(part.data_ptr()), st))
+        packed += part
+    torch.cuda.synchronize()
+    Fh, Zh = F.cpu().numpy(), Z.cpu().numpy()
+    Gd = packed[:K * K].cpu().numpy().reshape(K, K, order="F")
+    Cd = packed[K * K:K * K + K * T].cpu().numpy().reshape(K, T, order="F")
+    assert relmax(Gd, Fh.T @ Fh) < 1e-12 and relmax(Cd, Fh.T @ Zh) < 1e-12
+    assert abs(packed[-1].item() - np.sum(Zh * Zh)) / np.sum(Zh * Zh) < 1e-13
+    # (2) fused: chunks of 8192 rows, basis never stored
+    fused = torch.empty(plen, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib.frk_plan_predict_gram_dev(plan._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(Z.data_ptr()), T, n,
+                                                  C.c_void_p(fused.data_ptr()), 8192, st))
+    torch.cuda.synchronize()
+    assert relmax(fused.cpu().numpy(), packed.cpu().numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("n,K,T,s", [(4000, 12, 5, 0.0), (20000, 60, 20, 0.0), (3000, 40, 1, 0.0), (5000, 25, 8, 0.5)])
+def test_cMLEimat_matches_oracle(n, K, T, s):
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    F, Z = _data(n, K, T, seed=K)
+    ref = O.cMLEimat(F, Z, s, wSave=True)            # the literal sequence of n-sized products
+    got = G.cMLEimat(F, Z, s, wSave=True)
+    assert abs(got["v"] - ref["v"]) <= TOL * abs(ref["v"])
+    assert abs(got["negloglik"] - ref["negloglik"]) <= TOL * abs(ref["negloglik"])
+    assert relmax(got["M"], ref["M"]) < TOL
+    assert relmax(got["w"], ref["w"]) < 1e-9           # the reference's own cancellation ~ dhat/v
+    # V: the literal formula is numerically unstable; strict against the closed form, loose vs literal
+    Gs, Cs, zz = O.gram_stats(F, Z)
+    closed = O.cmle_from_stats(Gs, Cs, zz, n, T, s=s, wSave=True)
+    assert relmax(got["V"], closed["V"]) < 1e-9
+    assert relmax(got["V"], ref["V"]) < 1e-3
+    assert np.array_equal(got["M"], got["M"].T)
+    only = G.cMLEimat(F, Z, s)                         # onlylogLike = !wSave
+    assert set(only) == {"negloglik"} and only["negloglik"] == got["negloglik"]
+
+
+def test_getHalf_getEigen_cMLE():
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    n, K, T = 6000, 35, 6
+    F, Z = _data(n, K, T, seed=9)
+    half_ref = O.getHalf(F, F)
+    half = G.getHalf(F, F)
+    assert relmax(half, half_ref) < TOL
+    iDF = F * np.linspace(0.5, 2.0, n)[:, None]        # a diagonal-D weighting: t(Fk) %*% iDFk path
+    assert relmax(G.getHalf(F, iDF), O.getHalf(F, iDF)) < 1e-9
+    e_ref, e = O.getEigen(F.T @ F), G.getEigen(F.T @ F)
+    assert relmax(e["value"], e_ref["value"]) < 1e-12 and np.all(np.diff(e["value"]) <= 0)
+    # cMLE given half and JSJ (selectBasis' inner call, R/autoFRK.R:306-316)
+    t = half_ref @ F.T @ Z
+    JSJ = (t @ t.T) / T
+    JSJ = (JSJ + JSJ.T) / 2
+    trS = np.sum(Z * Z) / T
+    r1, g1 = O.cMLE(F, T, trS, half_ref, JSJ), G.cMLE(F, T, trS, half_ref, JSJ)
+    assert abs(g1["negloglik"] - r1["negloglik"]) <= TOL * abs(r1["negloglik"])
+    r2, g2 = O.cMLE(F, T, trS, half_ref, JSJ, wSave=True), G.cMLE(F, T, trS, half_ref, JSJ, wSave=True)
+    assert abs(g2["v"] - r2["v"]) <= TOL * abs(r2["v"]) and relmax(g2["M"], r2["M"]) < TOL
+    assert g2["L"].shape == r2["L"].shape
+    assert relmax(g2["L"] @ g2["L"].T @ F[:, :3], r2["L"] @ r2["L"].T @ F[:, :3]) < 1e-9   # L up to column signs
+    r3, g3 = O.cMLE(F, T, trS, half_ref, JSJ, vfixed=0.7, wSave=True), G.cMLE(F, T, trS, half_ref, JSJ, vfixed=0.7, wSave=True)
+    assert g3["v"] == 0.7 and relmax(g3["M"], r3["M"]) < TOL
+
+
+def test_sol_v_branches_through_cMLE():
+    """the piecewise rule for v (R/autoFRK.R:335-351), driven through crafted diagonal JSJ matrices."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(4)
+    for n, d, trS in [(50, [0.5, 0.2, 0.1], 100.0),      # max(d) < trS/n  -> first branch
+                      (50, [30.0, 5.0, 0.1], 60.0),      # general branch, L in the middle
+                      (3, [9.0, 5.0, 2.0], 17.0),        # k == n corner (ks[n] <- n-1, L == n)
+                      (40, [8.0, 8.0, 8.0, 1e-9], 30.0)]:
+        k = len(d)
+        F = rng.standard_normal((n, k))
+        JSJ = np.diag(np.array(d, dtype=float))
+        half = np.eye(k)
+        ref = O.cMLE(F, 2, trS, half, JSJ, wSave=True)
+        got = G.cMLE(F, 2, trS, half, JSJ, wSave=True)
+        assert abs(got["v"] - ref["v"]) <= 1e-12 * max(1.0, abs(ref["v"])), (n, d)
+        assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-12 * abs(ref["negloglik"])
+        assert relmax(got["M"], ref["M"]) < 1e-12
+
+
+def test_autoFRK_config1_and_predict_FRK():
+    """BASELINE configs[0]: autoFRK(Data=z, loc=s) on 2,000 random 2-D locations, 1 replicate, default mrts basis."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(0)
+    n = 2000
+    loc = rng.random((n, 2))
+    f = np.sin(4 * loc[:, 0]) * np.cos(3 * loc[:, 1]) + 0.5 * loc[:, 0]
+    z = (f * 3.0 + rng.standard_normal(n)).reshape(-1, 1)
+    ref = O.autoFRK(z, loc)
+    got = G.autoFRK(z, loc)
+    Kr, Kg = ref["G"].X.shape[1], got["G"].X.shape[1]
+    assert np.array_equal(got["G"].Kgrid, ref["G"].extra["Kgrid"]) and len(got["G"].Kgrid) == 30 and got["G"].Kgrid.max() == 446
+    assert relmax(got["G"].AIC, ref["G"].extra["AIC"]) < 1e-8
+    assert Kg == Kr
+    assert abs(got["s"] - ref["s"]) <= 1e-8 * abs(ref["s"])
+    assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-8 * abs(ref["negloglik"])
+    # fitted surface is invariant to the eigenvector signs: compare G M G' action and the kriging predictor
+    newloc = rng.random((1500, 2))
+    pr = O.predict_FRK(ref, newloc=newloc, se_report=True)
+    pg = G.predict_FRK(got, newloc=newloc, se_report=True)
+    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-7
+    assert relmax(pg["se"], pr["se"]) < 1e-6
+    # newloc = NULL: basis <- object$G
+    p0r, p0g = O.predict_FRK(ref), G.predict_FRK(got)
+    assert relmax(p0g["pred.value"], p0r["pred.value"]) < 1e-7
+
+
+def test_autoFRK_multi_replicate_with_given_basis():
+    """T = 20 replicates, user-supplied G = mrts(knot, K, loc) (the large-config calling convention)."""
+    import oracle as O
+    from autofrk_b200 import frk as G, mrts as GM
+
+    rng = np.random.default_rng(1)
+    n, T, K = 3000, 20, 40
+    loc = rng.random((n, 2))
+    knot = loc[:400]
+    Fo = O.mrts(knot, K, loc)
+    Fg = GM.MrtsBasis(Fo.X, Fo.UZ, Fo.Xu, Fo.nconst, Fo.BBBH)       # same basis on both sides: sign-free comparison
+    wt = rng.standard_normal((2, T)) * np.array([[5.0], [3.0]])
+    Z = Fo.X[:, 3:5] @ wt + rng.standard_normal((n, T))
+    ref = O.autoFRK(Z, loc, G=Fo)
+    got = G.autoFRK(Z, loc, G=Fg)
+    assert abs(got["s"] - ref["s"]) <= TOL * abs(ref["s"])
+    assert relmax(got["M"], ref["M"]) < TOL
+    assert relmax(got["w"], ref["w"]) < 1e-9
+    newloc = rng.random((2000, 2))
+    pr = O.predict_FRK(ref, newloc=newloc, se_report=True)
+    pg = G.predict_FRK(got, newloc=newloc, se_report=True)
+    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-9
+    assert pg["se"].shape == pr["se"].shape == (2000, T)
+    # se is checked against the closed-form V (the literal V is unstable)
+    Gs, Cs, zz = O.gram_stats(Fo.X, Z)
+    closed = O.cmle_from_stats(Gs, Cs, zz, n, T, wSave=True)
+    B = O.predict_mrts(Fo, newloc)
+    se_closed = np.sqrt(np.maximum(0, np.sum((B @ closed["V"]) * B, axis=1)))
+    assert relmax(pg["se"][:, 0], se_closed) < 1e-8

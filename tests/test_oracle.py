@@ -1,0 +1,161 @@
+"""CPU-only checks that pin down the oracle itself (PARITY UNPINNED by the reference: it ships no tests).
+
+Two independent codings (numpy vs plain C), 50-digit arithmetic on a small case, the algebraic identities
+of SURVEY.md section 4, and the committed golden vectors."""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle.mrts_oracle import tpm2, tpm_predict, xobs_diag_of
+from util import colrel, relmax
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def clib():
+    from autofrk_b200 import build
+
+    lib = C.CDLL(str(build.build_oracle()))
+    lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+    lib.oracle_tpm2.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.oracle_predict_x1.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_int, C.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_c_and_numpy_restatements_agree(clib, d):
+    rng = np.random.default_rng(d)
+    m, n2 = 57, 203
+    Xu = np.asfortranarray(rng.random((m, d)))
+    xn = np.asfortranarray(rng.random((n2, d)))
+    xn[:4] = Xu[:4]
+    L = np.empty((n2, m), order="F")
+    assert clib.oracle_tpm_predict(xn.ctypes.data, n2, n2, Xu.ctypes.data, m, d, L.ctypes.data, n2) == 0
+    ref = tpm_predict(xn, Xu, d)
+    assert np.max(np.abs(L - ref)) <= 4e-16 * np.max(np.abs(ref))
+    assert np.all(L[:4][np.arange(4), np.arange(4)] == 0.0)          # r == 0
+    H = np.empty((m, m), order="F")
+    assert clib.oracle_tpm2(Xu.ctypes.data, m, d, H.ctypes.data) == 0
+    assert np.max(np.abs(H - tpm2(Xu, d))) <= 4e-16 * np.max(np.abs(H))
+    assert np.array_equal(H, H.T) and np.all(np.diag(H) == 0)
+    kstar = 12
+    fit = O.mrtsrcpp(Xu, xobs_diag_of(Xu, m), kstar)
+    UZ, BBBH = np.asfortranarray(fit["UZ"]), np.asfortranarray(fit["BBBH"])
+    X1 = np.empty((n2, kstar), order="F")
+    assert clib.oracle_predict_x1(Xu.ctypes.data, m, d, xn.ctypes.data, n2, BBBH.ctypes.data, UZ.ctypes.data, UZ.shape[0],
+                                  kstar, X1.ctypes.data) == 0
+    ref1 = O.mrtsrcpp_predict(Xu, None, xn, BBBH, UZ, fit["nconst"], kstar)["X1"]
+    assert colrel(X1, ref1) < 1e-11
+    assert clib.oracle_tpm_predict(xn.ctypes.data, n2, n2, Xu.ctypes.data, m, 4, L.ctypes.data, n2) == 1
+
+
+def test_kernel_against_50_digit_arithmetic():
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    rng = np.random.default_rng(0)
+    for d in (1, 2, 3):
+        Xu, xn = rng.random((6, d)), rng.random((5, d))
+        got = tpm_predict(xn, Xu, d)
+        for i in range(5):
+            for j in range(6):
+                r = mp.sqrt(sum((mp.mpf(xn[i, c]) - mp.mpf(Xu[j, c])) ** 2 for c in range(d)))
+                exact = {1: r ** 3 / 12, 2: r * r * mp.log(r) / (8 * mp.pi), 3: -r / 8}[d]
+                # a few ulp of the O(0.1) kernel scale (near r = 1 the d=2 kernel crosses zero, so not relative)
+                assert abs(got[i, j] - float(exact)) <= 5e-17
+
+
+@pytest.mark.parametrize("d,m,kstar", [(1, 30, 8), (2, 200, 50), (3, 150, 40)])
+def test_identities_of_the_reference_algorithm(d, m, kstar):
+    """predict at the knots reproduces the fit; eigen-columns orthonormal and orthogonal to [1, Xu]."""
+    rng = np.random.default_rng(m)
+    Xu = rng.random((m, d))
+    xd = xobs_diag_of(Xu, m)
+    fit = O.mrtsrcpp(Xu, xd, kstar)
+    K = kstar + d + 1
+    assert fit["X"].shape == (m, K) and fit["UZ"].shape == (m + d + 1, K) and fit["BBBH"].shape == (d + 1, m)
+    at = O.mrtsrcpp_predict(Xu, xd, Xu, fit["BBBH"], fit["UZ"], fit["nconst"], K)
+    assert np.all(at["X1"][:, kstar:] == 0.0)                                  # quirk 1: trailing d+1 zero columns
+    assert colrel(at["X1"][:, :kstar], fit["X"][:, d + 1:]) < 1e-10
+    g = fit["X"][:, d + 1:]
+    assert np.max(np.abs(g.T @ g / m - np.eye(kstar))) < 1e-12
+    B = np.column_stack([np.ones(m), Xu])
+    assert np.max(np.abs(B.T @ g)) < 1e-9
+    assert at["X"] is not None and np.array_equal(at["X"], Xu)                 # quirk 4
+    assert np.allclose(fit["nconst"], Xu.std(axis=0))                          # population sd (quirk 5)
+    p0 = O.mrtsrcpp_predict0(Xu, xd, Xu[:10], kstar)
+    assert colrel(p0["X1"], at["X1"][:10, :kstar]) < 1e-12
+    # R front-ends
+    obj = O.mrts(Xu, K)
+    assert colrel(O.predict_mrts(obj, Xu), obj.X) < 1e-10
+    with pytest.raises(ValueError, match="k must be less than n"):
+        O.mrtsrcpp(Xu, xd, m)
+    with pytest.raises(ValueError, match="xobs_diag must be"):
+        O.mrtsrcpp(Xu, np.eye(d + 1), kstar)
+    with pytest.raises(ValueError, match="UZ dimensions are inconsistent"):
+        O.mrtsrcpp_predict(Xu, xd, Xu, fit["BBBH"], fit["UZ"], fit["nconst"], K + 1)
+
+
+def test_fit_depends_on_data_only_through_sufficient_statistics():
+    """literal cMLEimat (R/autoFRK.R:399-480) == the (G, C, zz) restatement the CUDA path evaluates."""
+    rng = np.random.default_rng(3)
+    n, K, T = 4000, 12, 5
+    F = rng.standard_normal((n, K))
+    F[:, 0] = 1.0
+    wts = np.zeros((K, T))
+    wts[:3] = rng.standard_normal((3, T)) * 3
+    Z = F @ wts + rng.standard_normal((n, T))
+    lit = O.cMLEimat(F, Z, 0.0, wSave=True)
+    st = O.cmle_from_stats(*O.gram_stats(F, Z), n, T, wSave=True)
+    assert abs(lit["v"] - st["v"]) < 1e-12 * abs(st["v"])
+    assert abs(lit["negloglik"] - st["negloglik"]) < 1e-12 * abs(st["negloglik"])
+    assert relmax(lit["M"], st["M"]) < 1e-11
+    assert relmax(lit["w"], st["w"]) < 1e-9
+    assert relmax(lit["V"], st["V"]) < 1e-4              # literal V cancels catastrophically
+    # invCz is the Woodbury inverse
+    L = rng.standard_normal((50, 4))
+    z = rng.standard_normal((50, 2))
+    R = np.diag(rng.random(50) + 0.5)
+    assert relmax(O.invCz(R, L, z), np.linalg.solve(R + L @ L.T, z)) < 1e-12
+    assert relmax(O.invCz(np.diag(R).copy(), L, z), np.linalg.solve(R + L @ L.T, z)) < 1e-12
+    assert relmax(O.ZinvC(R, L, z.T), np.linalg.solve(R + L @ L.T, z).T) < 1e-12
+
+
+def test_sol_v_and_kgrid():
+    assert O.sol_v([0.5, 0.2], 0.0, 100.0, 50) == 2.0
+    assert O.sol_v([0.5, 0.2], 3.0, 100.0, 50) == 0.0
+    v = O.sol_v([30.0, 5.0, 0.1], 0.0, 60.0, 50)
+    assert abs(v - (60.0 - 35.0) / 48) < 1e-15      # L = 2
+    assert O.sol_v([9.0, 5.0, 2.0], 0.0, 17.0, 3) == max((17.0 - 14.0) / 1 - 0, 0)
+    from oracle.frk_oracle import kgrid
+    K = kgrid(2, 447)                                     # BASELINE configs[0]: N = 2000 -> klim = 447
+    assert len(K) == 30 and K[0] == 3 and K[-1] == 446
+
+
+def test_getLikelihood_complete_data_equals_neg2llik():
+    rng = np.random.default_rng(8)
+    n, K, T = 300, 6, 3
+    F = rng.standard_normal((n, K))
+    Z = F[:, :2] @ rng.standard_normal((2, T)) * 2 + rng.standard_normal((n, T))
+    fit = O.cMLEimat(F, Z, 0.0, wSave=True)
+    ll = O.getLikelihood(Z, F, fit["M"], fit["v"], np.ones(n))
+    assert abs(ll - fit["negloglik"]) < 1e-8 * abs(fit["negloglik"])
+
+
+def test_golden_vectors():
+    """committed fixtures (tests/golden/make_golden.py): regression pins for the oracle, since the reference has none."""
+    gold = np.load(ROOT / "tests" / "golden" / "mrts_small.npz")
+    meta = json.loads((ROOT / "tests" / "golden" / "mrts_small.json").read_text())
+    for case in meta["cases"]:
+        tag, d, kstar = case["tag"], case["d"], case["kstar"]
+        Xu, xnew = gold[f"{tag}_Xu"], gold[f"{tag}_xnew"]
+        fit = O.mrtsrcpp(Xu, xobs_diag_of(Xu, Xu.shape[0]), kstar)
+        assert relmax(fit["BBBH"], gold[f"{tag}_BBBH"]) < 1e-12
+        assert relmax(fit["nconst"], gold[f"{tag}_nconst"]) < 1e-14
+        X1 = O.mrtsrcpp_predict(Xu, None, xnew, gold[f"{tag}_BBBH"], gold[f"{tag}_UZ"], gold[f"{tag}_nconst"], kstar)["X1"]
+        assert colrel(X1, gold[f"{tag}_X1"]) < 1e-12

@@ -1,0 +1,38 @@
+"""Quick K4 timing probe (device-resident F, Z).  Measurement tooling."""
+import ctypes as C
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from autofrk_b200 import _lib
+
+
+def run(n, K, T, reps=3):
+    F = torch.randn((K, n), dtype=torch.float64, device="cuda").T
+    Z = torch.randn((max(T, 1), n), dtype=torch.float64, device="cuda").T
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    packed = torch.empty(plen, dtype=torch.float64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def go():
+        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, n, C.c_void_p(Z.data_ptr()), T, n,
+                                               C.c_void_p(packed.data_ptr()), st))
+    go()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); go(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    flops = n * K * (K + 1.0) + 2.0 * n * K * T + 2.0 * n * T
+    res = dict(n=n, K=K, T=T, ms=best, tflops_credited=flops / best / 1e9, gbs=8.0 * n * (K + T) / best / 1e6)
+    print(json.dumps(res), flush=True)
+    return res
+
+
+if __name__ == "__main__":
+    out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(5_000_000, 32, 4), run(1_000_000, 1000, 100),
+           run(5_000_000, 200, 20)]
+    json.dump(out, open("gpurun_out/gram_probe.json", "w"), indent=1)
