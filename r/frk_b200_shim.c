@@ -1,0 +1,151 @@
+/* .Call shim binding autoFRK's four registered native routines (src/RcppExports.cpp:71-77) to
+ * libfrk_b200.so.  Written against R's C API only (Rinternals.h); NOT compiled in the build
+ * container (R is not installed there) -- the identical C ABI is exercised through ctypes.
+ *
+ * Build inside the package:   PKG_LIBS = -L$(FRK_B200_HOME)/autofrk_b200 -lfrk_b200
+ *                             PKG_CPPFLAGS = -I$(FRK_B200_HOME)/include
+ * and drop src/autoFRK.cpp + src/RcppExports.cpp (this file replaces both; LinkingTo: Rcpp,
+ * RcppEigen, RSpectra are no longer needed).
+ *
+ * Conventions honoured: arguments are REALSXP matrices read in place (column-major,
+ * dims from the dim attribute; integer input is an error exactly as with Eigen::Map<MatrixXd>),
+ * results are freshly allocated named lists, errors leave through Rf_error() after every native
+ * resource has been released (the library never throws across the C ABI).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+#include "frk_b200.h"
+
+static void need_real_matrix(SEXP x, const char *what) {
+    if (TYPEOF(x) != REALSXP) Rf_error("Wrong R type for mapped matrix");   /* RcppEigen's message */
+    if (!Rf_isMatrix(x) && XLENGTH(x) > 0 && what[0] != 'n') (void)what;
+}
+static R_xlen_t nrow_of(SEXP x) { return Rf_isMatrix(x) ? Rf_nrows(x) : XLENGTH(x); }
+static int ncol_of(SEXP x) { return Rf_isMatrix(x) ? Rf_ncols(x) : 1; }
+static void check(int32_t status) { if (status != FRK_OK) Rf_error("%s", frk_last_error()); }
+
+static SEXP named_list(int n, const char **names) {
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, n));
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, n));
+    for (int i = 0; i < n; i++) SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+
+/* getASCeigens(A) -> list(value, vector)                       src/autoFRK.cpp:24-32 */
+SEXP _autoFRK_getASCeigens(SEXP A) {
+    need_real_matrix(A, "A");
+    int n = Rf_nrows(A);
+    const char *names[] = {"value", "vector"};
+    SEXP out = PROTECT(named_list(2, names));
+    SEXP value = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP vector = PROTECT(Rf_allocMatrix(REALSXP, n, n));
+    check(frk_getASCeigens(REAL(A), n, REAL(value), REAL(vector)));
+    SET_VECTOR_ELT(out, 0, value);
+    SET_VECTOR_ELT(out, 1, vector);
+    UNPROTECT(3);
+    return out;
+}
+
+/* mrtsrcpp(Xu, xobs_diag, k) -> list(X, UZ, BBBH, nconst)       src/autoFRK.cpp:224-242 */
+SEXP _autoFRK_mrtsrcpp(SEXP Xu, SEXP xobs_diag, SEXP k_) {
+    need_real_matrix(Xu, "Xu"); need_real_matrix(xobs_diag, "xobs_diag");
+    int64_t n = nrow_of(Xu); int d = ncol_of(Xu); int k = Rf_asInteger(k_);
+    int kk = k > 0 ? k : 0;
+    const char *names[] = {"X", "UZ", "BBBH", "nconst"};
+    SEXP out = PROTECT(named_list(4, names));
+    SEXP X = PROTECT(Rf_allocMatrix(REALSXP, (int)n, kk + d + 1));
+    SEXP UZ = PROTECT(Rf_allocMatrix(REALSXP, (int)n + d + 1, kk + d + 1));
+    SEXP BBBH = PROTECT(Rf_allocMatrix(REALSXP, d + 1, (int)n));
+    SEXP nconst = PROTECT(Rf_allocVector(REALSXP, d));
+    check(frk_mrtsrcpp(REAL(Xu), n, d, REAL(xobs_diag), (int)nrow_of(xobs_diag), ncol_of(xobs_diag), k,
+                       REAL(X), REAL(UZ), REAL(BBBH), REAL(nconst)));
+    SET_VECTOR_ELT(out, 0, X); SET_VECTOR_ELT(out, 1, UZ); SET_VECTOR_ELT(out, 2, BBBH); SET_VECTOR_ELT(out, 3, nconst);
+    UNPROTECT(5);
+    return out;
+}
+
+/* mrtsrcpp_predict0(Xu, xobs_diag, xnew, k) -> list(X, UZ, BBBH, nconst, X1)   src/autoFRK.cpp:248-281 */
+SEXP _autoFRK_mrtsrcpp_predict0(SEXP Xu, SEXP xobs_diag, SEXP xnew, SEXP k_) {
+    need_real_matrix(Xu, "Xu"); need_real_matrix(xobs_diag, "xobs_diag"); need_real_matrix(xnew, "xnew");
+    int64_t n = nrow_of(Xu), n2 = nrow_of(xnew); int d = ncol_of(Xu); int k = Rf_asInteger(k_);
+    int kk = k > 0 ? k : 0;
+    const char *names[] = {"X", "UZ", "BBBH", "nconst", "X1"};
+    SEXP out = PROTECT(named_list(5, names));
+    SEXP X = PROTECT(Rf_allocMatrix(REALSXP, (int)n, kk + d + 1));
+    SEXP UZ = PROTECT(Rf_allocMatrix(REALSXP, (int)n + d + 1, kk + d + 1));
+    SEXP BBBH = PROTECT(Rf_allocMatrix(REALSXP, d + 1, (int)n));
+    SEXP nconst = PROTECT(Rf_allocVector(REALSXP, d));
+    SEXP X1 = PROTECT(Rf_allocMatrix(REALSXP, (int)n2, kk));
+    check(frk_mrtsrcpp_predict0(REAL(Xu), n, d, REAL(xobs_diag), (int)nrow_of(xobs_diag), ncol_of(xobs_diag),
+                                REAL(xnew), n2, ncol_of(xnew), k, REAL(X), REAL(UZ), REAL(BBBH), REAL(nconst), REAL(X1)));
+    SET_VECTOR_ELT(out, 0, X); SET_VECTOR_ELT(out, 1, UZ); SET_VECTOR_ELT(out, 2, BBBH);
+    SET_VECTOR_ELT(out, 3, nconst); SET_VECTOR_ELT(out, 4, X1);
+    UNPROTECT(6);
+    return out;
+}
+
+/* mrtsrcpp_predict(Xu, xobs_diag, xnew, BBBH, UZ, nconst, k) -> list(X = Xu, UZ, BBBH, nconst, X1)
+ * src/autoFRK.cpp:287-326; the first four members are the caller's own objects (:320-323). */
+SEXP _autoFRK_mrtsrcpp_predict(SEXP Xu, SEXP xobs_diag, SEXP xnew, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP k_) {
+    need_real_matrix(Xu, "Xu"); need_real_matrix(xnew, "xnew"); need_real_matrix(BBBH, "BBBH");
+    need_real_matrix(UZ, "UZ"); need_real_matrix(nconst, "nconst");
+    int64_t n = nrow_of(Xu), n2 = nrow_of(xnew); int d = ncol_of(Xu); int k = Rf_asInteger(k_);
+    const char *names[] = {"X", "UZ", "BBBH", "nconst", "X1"};
+    SEXP out = PROTECT(named_list(5, names));
+    SEXP X1 = PROTECT(Rf_allocMatrix(REALSXP, (int)n2, k > 0 ? k : 0));
+    check(frk_mrtsrcpp_predict(REAL(Xu), n, d, TYPEOF(xobs_diag) == REALSXP ? REAL(xobs_diag) : NULL, REAL(xnew), n2,
+                               ncol_of(xnew), REAL(BBBH), nrow_of(BBBH), ncol_of(BBBH), REAL(UZ), nrow_of(UZ),
+                               ncol_of(UZ), REAL(nconst), XLENGTH(nconst), k, REAL(X1)));
+    SET_VECTOR_ELT(out, 0, Xu); SET_VECTOR_ELT(out, 1, UZ); SET_VECTOR_ELT(out, 2, BBBH);
+    SET_VECTOR_ELT(out, 3, nconst); SET_VECTOR_ELT(out, 4, X1);
+    UNPROTECT(2);
+    return out;
+}
+
+/* new: frk_gram_stats(Fk, Data) -> list(G, C, zz); frk_cMLEimat_stats(G, C, zz, n, TT, s, wSave) -> list(v, M, s, negloglik[, w, V]) */
+SEXP _autoFRK_gram_stats(SEXP Fk, SEXP Data) {
+    need_real_matrix(Fk, "Fk"); need_real_matrix(Data, "Data");
+    int64_t n = nrow_of(Fk); int K = ncol_of(Fk), T = ncol_of(Data);
+    const char *names[] = {"G", "C", "zz"};
+    SEXP out = PROTECT(named_list(3, names));
+    SEXP G = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    SEXP C = PROTECT(Rf_allocMatrix(REALSXP, K, T));
+    SEXP zz = PROTECT(Rf_allocVector(REALSXP, 1));
+    check(frk_gram_stats(REAL(Fk), n, K, REAL(Data), T, REAL(G), REAL(C), REAL(zz)));
+    SET_VECTOR_ELT(out, 0, G); SET_VECTOR_ELT(out, 1, C); SET_VECTOR_ELT(out, 2, zz);
+    UNPROTECT(4);
+    return out;
+}
+
+SEXP _autoFRK_cMLEimat_stats(SEXP G, SEXP C, SEXP zz, SEXP n_, SEXP s_, SEXP wSave_) {
+    int K = Rf_nrows(G), T = Rf_ncols(C), wsave = Rf_asLogical(wSave_);
+    const char *names[] = {"v", "M", "s", "negloglik", "w", "V"};
+    SEXP out = PROTECT(named_list(wsave ? 6 : 4, names));
+    SEXP v = PROTECT(Rf_allocVector(REALSXP, 1)), nll = PROTECT(Rf_allocVector(REALSXP, 1));
+    SEXP M = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    SEXP w = PROTECT(Rf_allocMatrix(REALSXP, K, T)), V = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    check(frk_cMLEimat_stats(REAL(G), K, REAL(C), K, Rf_asReal(zz), K, T, (int64_t)Rf_asReal(n_), Rf_asReal(s_), wsave, 0, 0,
+                             REAL(v), REAL(nll), REAL(M), wsave ? REAL(w) : NULL, wsave ? REAL(V) : NULL));
+    SET_VECTOR_ELT(out, 0, v); SET_VECTOR_ELT(out, 1, M); SET_VECTOR_ELT(out, 2, s_); SET_VECTOR_ELT(out, 3, nll);
+    if (wsave) { SET_VECTOR_ELT(out, 4, w); SET_VECTOR_ELT(out, 5, V); }
+    UNPROTECT(6);
+    return out;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_autoFRK_getASCeigens", (DL_FUNC)&_autoFRK_getASCeigens, 1},
+    {"_autoFRK_mrtsrcpp", (DL_FUNC)&_autoFRK_mrtsrcpp, 3},
+    {"_autoFRK_mrtsrcpp_predict0", (DL_FUNC)&_autoFRK_mrtsrcpp_predict0, 4},
+    {"_autoFRK_mrtsrcpp_predict", (DL_FUNC)&_autoFRK_mrtsrcpp_predict, 7},
+    {"_autoFRK_gram_stats", (DL_FUNC)&_autoFRK_gram_stats, 2},
+    {"_autoFRK_cMLEimat_stats", (DL_FUNC)&_autoFRK_cMLEimat_stats, 6},
+    {NULL, NULL, 0}};
+
+void R_init_autoFRK(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
