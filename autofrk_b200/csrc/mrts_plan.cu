@@ -1,5 +1,6 @@
 // Plan construction (W packing, Cpoly, zero-column detection) and the K1 launch logic.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "mrts_plan.cuh"
 
@@ -20,31 +21,30 @@ __global__ void column_nonzero_kernel(const double* __restrict__ UZ, int64_t ldu
 
 // Packed image of one slice: for every chunk of KC knots
 //   [q = 0..KC/4)[col = 0..BN)[t = 0..4)   W[chunk*KC + 4q + t][col0 + col]   (0 past m / past ncols)
-//   [kk = 0..KC)[c = 0..DP)                knot coordinates (knot 0 repeated past m: finite phi, W = 0)
-__global__ void pack_w_kernel(const double* __restrict__ UZ, int64_t ldu, const double* __restrict__ Xu,
-                              int64_t m, int d, int dp, int col0, int ncols, int bn, int kc, int nchunks,
-                              double* __restrict__ wpack) {
-    const int stage = kc * bn + kc * dp;
+__global__ void pack_w_kernel(const double* __restrict__ UZ, int64_t ldu, int64_t m, int col0, int ncols, int bn,
+                              int kc, int nchunks, double* __restrict__ wpack) {
+    const int stage = kc * bn;
     const int64_t total = int64_t(nchunks) * stage;
     for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
          idx += int64_t(gridDim.x) * blockDim.x) {
         const int chunk = int(idx / stage);
         const int r = int(idx % stage);
-        double v = 0.0;
-        if (r < kc * bn) {
-            const int q = r / (bn * 4), rem = r % (bn * 4);
-            const int col = rem >> 2, tt = rem & 3;
-            const int64_t j = int64_t(chunk) * kc + q * 4 + tt;
-            if (j < m && col < ncols) v = UZ[j + int64_t(col0 + col) * ldu];
-        } else {
-            const int rr = r - kc * bn;
-            const int kk = rr / dp, c = rr % dp;
-            int64_t j = int64_t(chunk) * kc + kk;
-            if (j >= m) j = 0;
-            if (c < d) v = Xu[j + int64_t(c) * m];
-        }
-        wpack[idx] = v;
+        const int q = r / (bn * 4), rem = r % (bn * 4);
+        const int col = rem >> 2, tt = rem & 3;
+        const int64_t j = int64_t(chunk) * kc + q * 4 + tt;
+        wpack[idx] = (j < m && col < ncols) ? UZ[j + int64_t(col0 + col) * ldu] : 0.0;
     }
+}
+
+// knot coordinates as DP-tuples, padded to nchunks*KC knots with knot 0 (finite phi, multiplied by W = 0)
+__global__ void pack_knots_kernel(const double* __restrict__ Xu, int64_t m, int d, int dp, int64_t npad,
+                                  double* __restrict__ knots) {
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= npad * dp) return;
+    int64_t j = idx / dp;
+    const int c = int(idx % dp);
+    if (j >= m) j = 0;
+    knots[idx] = (c < d) ? Xu[j + int64_t(c) * m] : 0.0;
 }
 
 // cpoly[a*bn + col] = sum_j BBBH[a, j] * W[j, col0+col]   (src/autoFRK.cpp:324, (BBBH) * UZ.block(0,0,n,k))
@@ -132,13 +132,24 @@ MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBB
         const int nslices = (ntile8 * 8 + max_bn - 1) / max_bn;
         const int per_slice = ((ntile8 + nslices - 1) / nslices) * 8;  // columns per slice, multiple of 8
         const PredictKernelInfo* best = nullptr;
-        for (int i = 0; i < nk; ++i)
+        for (int i = 0; i < nk; ++i)  // first match wins among equals: later table entries are experimental variants
             if (tab[i].bn >= per_slice && (!best || tab[i].bn < best->bn || (tab[i].bn == best->bn && tab[i].bm > best->bm)))
                 best = &tab[i];
+        if (const char* force = std::getenv("FRK_K1_CONFIG")) {  // tuning aid: index into the configuration table
+            const int i = std::atoi(force);
+            if (i >= 0 && i < nk && tab[i].bn >= per_slice) best = &tab[i];
+        }
         if (!best) fail(2, "internal: no K1 configuration for %d columns", per_slice);
         p->ki = best;
         best->prepare();
-        p->nchunks = int((m + best->kc - 1) / best->kc);
+        p->nchunks = std::max(best->min_chunks, int((m + best->kc - 1) / best->kc));
+        p->knots.alloc(size_t(p->nchunks) * best->kc * best->dp);
+        {
+            const int64_t npad = int64_t(p->nchunks) * best->kc;
+            pack_knots_kernel<<<unsigned((npad * best->dp + 255) / 256), 256, 0, st>>>(dXu, m, d, best->dp, npad,
+                                                                                     p->knots.p);
+            FRK_CUDA(cudaGetLastError());
+        }
 
         for (int s = 0; s < nslices; ++s) {
             PredictSlice sl;
@@ -147,8 +158,8 @@ MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBB
             if (sl.ncols <= 0) break;
             sl.wpack.alloc(size_t(p->nchunks) * best->stage_doubles);
             sl.cpoly.alloc(size_t(d + 1) * best->bn);
-            pack_w_kernel<<<p->sm_count * 4, 256, 0, st>>>(dUZ, ldu, dXu, m, d, best->dp, sl.col0, sl.ncols,
-                                                           best->bn, best->kc, p->nchunks, sl.wpack.p);
+            pack_w_kernel<<<p->sm_count * 4, 256, 0, st>>>(dUZ, ldu, m, sl.col0, sl.ncols, best->bn, best->kc,
+                                                           p->nchunks, sl.wpack.p);
             FRK_CUDA(cudaGetLastError());
             const int nthr = (d + 1) * best->bn;
             cpoly_kernel<<<(nthr + 127) / 128, 128, 0, st>>>(dBBBH, dUZ, ldu, m, d, sl.col0, sl.ncols, best->bn,
@@ -189,6 +200,7 @@ static void predict_cols(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t l
         a.ldx = ldx;
         a.n2 = n2;
         a.wpack = sl.wpack.p;
+        a.knots = p->knots.p;
         a.nchunks = p->nchunks;
         a.cpoly = sl.cpoly.p;
         a.out = dout + int64_t(sl.col0) * ldo;

@@ -25,6 +25,7 @@ struct MrtsPlan {
     int nchunks = 0;
     const PredictKernelInfo* ki = nullptr;
     std::vector<PredictSlice> slices;
+    DevBuf<double> knots;   // nchunks * KC coordinate tuples (shared by all slices)
     double shift[3] = {0, 0, 0};   // colMeans(Xu)        R/autoFRK.R:1462
     double nconst[3] = {1, 1, 1};  // attr(obj,"nconst")  R/autoFRK.R:1464
     bool has_nconst = false;

@@ -10,14 +10,16 @@
 //     (tcgen05 / TMEM have no f64 kind).
 //   * W is pre-packed once per plan into the exact shared-memory image of a chunk
 //     ([k4-group][column][4 knots], followed by the chunk's knot coordinates) so that
-//       - one TMA bulk copy (cp.async.bulk -> UBLKCP) per chunk stages W + knots, tracked by an
-//         mbarrier, NSTAGE deep,
+//       - one TMA bulk copy (cp.async.bulk -> UBLKCP) per chunk stages W, tracked by an mbarrier,
+//         NSTAGE deep, refilled by whichever warp is last to finish with a stage,
 //       - every B-fragment load is a contiguous, conflict-free 256 B LDS.64 per warp.
 //   * The FP64 ALU and the DMMA unit share one pipe on B200 (measured: profiles/fp64_peaks_r01.json),
 //     so kernel evaluation is pure overhead on the binding resource.  Every thread therefore
 //     evaluates the same number of Phi values for chunk c+1 INSIDE the DMMA block of chunk c (one
 //     basic block, branch-free table log for d = 2), letting the scheduler drop the Phi arithmetic
 //     into the issue slots between dependent-free DMMAs instead of serialising it in front of them.
+//   * no CTA-wide barrier in the steady state: Phi is produced two chunks ahead and handed over through
+//     mbarriers, so warps drift up to a chunk apart and the pipe does not drain at chunk boundaries.
 //   * persistent CTAs (one per SM), tiles of BM rows dealt round-robin.
 #pragma once
 #include "frk_common.cuh"
@@ -35,24 +37,29 @@ struct PredictCfg {
     static constexpr int BN = WC * NT * 8;        // columns per slice (padded)
     static constexpr int KQ = KC / 4;             // k4 groups per chunk
     static constexpr int VPT = (BM * KC + NTHREADS - 1) / NTHREADS;  // Phi values per thread per chunk
-    static constexpr int STAGE_DOUBLES = KC * BN + KC * DP;
+    static constexpr int STAGE_DOUBLES = KC * BN;   // packed W chunk: [k4 group][column][4 knots]
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
     static constexpr int PHI_DOUBLES = BM * KC;
     static constexpr int XS_DOUBLES = BM * DP;
     static constexpr int LOGTAB_DOUBLES = (D == 2) ? 256 : 0;
-    static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + 2 * PHI_DOUBLES * 8 + 2 * XS_DOUBLES * 8 +
-                                         LOGTAB_DOUBLES * 8 + NSTAGE * 8;
+    static constexpr int AHEAD = 2;               // Phi is produced this many chunks ahead of its DMMAs
+    static constexpr int NPB = 4;                 // Phi chunk buffers (>= 2 * AHEAD)
+    static constexpr int MIN_CHUNKS = 4;          // the plan pads the knot list to at least this many chunks
+    static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + NPB * PHI_DOUBLES * 8 + 2 * XS_DOUBLES * 8 +
+                                         LOGTAB_DOUBLES * 8 + (NSTAGE + NPB) * 8 + NSTAGE * 4 + 16;
     static_assert(KC % 4 == 0, "KC must be a multiple of the DMMA k (4)");
     static_assert(STAGE_BYTES % 16 == 0, "TMA bulk copies need 16 B multiples");
     static_assert(NTHREADS <= 1024, "too many warps");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(NPB == 4 && AHEAD == 2, "the Phi ring uses pb ^ AHEAD");
 };
 
 struct PredictArgs {
     const double* xnew;   // n2 x d, column-major, leading dimension ldx
     int64_t ldx;
     int64_t n2;
-    const double* wpack;  // nchunks * STAGE_DOUBLES (packed W + knot coordinates)
+    const double* wpack;  // nchunks * STAGE_DOUBLES (packed W)
+    const double* knots;  // nchunks * KC * DP knot coordinates (tuples of DP doubles), padded with knot 0
     int nchunks;
     const double* cpoly;  // (d+1) x BN, row-major, zero padded:  BBBH * W
     double* out;          // n2 x ncols, column-major, leading dimension ldo
@@ -136,13 +143,18 @@ template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const PredictArgs a) {
     constexpr int D = C::D, DP = C::DP, BM = C::BM, BN = C::BN, KC = C::KC, KQ = C::KQ;
     constexpr int MT = C::MT, NT = C::NT, NSTAGE = C::NSTAGE, NTHREADS = C::NTHREADS, VPT = C::VPT;
+    constexpr int NPB = C::NPB, NWARPS = C::NWARPS, AHEAD = C::AHEAD;
+    constexpr int PHI_Q = (KQ >= 3) ? 1 : 0;  // k4-group after which the Phi arithmetic is placed in the source
+    constexpr bool PREFETCH = (VPT <= 2);     // knots one iteration early in registers (if they are affordable)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const stage0 = reinterpret_cast<double*>(smem_raw);
     double* const phib = stage0 + size_t(NSTAGE) * C::STAGE_DOUBLES;
-    double* const xs = phib + 2 * C::PHI_DOUBLES;
+    double* const xs = phib + NPB * C::PHI_DOUBLES;
     double* const logtab_d = xs + 2 * C::XS_DOUBLES;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(logtab_d + C::LOGTAB_DOUBLES);
+    uint64_t* const w_full = reinterpret_cast<uint64_t*>(logtab_d + C::LOGTAB_DOUBLES);  // TMA landed
+    uint64_t* const phi_full = w_full + NSTAGE;    // all warps stored their part of a Phi chunk
+    uint32_t* const w_done = reinterpret_cast<uint32_t*>(phi_full + NPB);  // warps done with a W stage
     const double2* const logtab = reinterpret_cast<const double2*>(logtab_d);
 
     const int tid = threadIdx.x;
@@ -152,17 +164,21 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
 
     if (int64_t(blockIdx.x) >= a.ntiles) return;
     const int64_t ntl = (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // tiles of this CTA
-    const int nchunks = a.nchunks;
+    const int nchunks = a.nchunks;        // >= 4 (the plan pads with zero-weight chunks)
     const int64_t total = ntl * nchunks;  // (tile, chunk) iterations of this CTA
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&w_full[s], 1);
+            w_done[s] = 0;
+        }
+        for (int b = 0; b < NPB; ++b) mbar_init(&phi_full[b], NWARPS);
         mbar_fence_init();
         for (int s = 0; s < NSTAGE; ++s)
             if (s < total) {
-                mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                mbar_expect_tx(&w_full[s], C::STAGE_BYTES);
                 tma_bulk_g2s(stage0 + size_t(s) * C::STAGE_DOUBLES,
-                             a.wpack + size_t(s % nchunks) * C::STAGE_DOUBLES, C::STAGE_BYTES, &full[s]);
+                             a.wpack + size_t(s % nchunks) * C::STAGE_DOUBLES, C::STAGE_BYTES, &w_full[s]);
             }
     }
     if constexpr (D == 2) {
@@ -193,21 +209,22 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
         phi_kk[i] = (vv / (BM * 4)) * 4 + (vv & 3);
     }
     double px[VPT][3], pu[VPT][3];  // coordinates of the pending Phi evaluations
-    auto phi_load = [&](int64_t it, int xbuf) {
-        const int s = int(it % NSTAGE);
-        const double* knots = stage0 + size_t(s) * C::STAGE_DOUBLES + KC * BN;
+    auto knots_load = [&](int chunk, double (&dst)[VPT][3]) {
+        const double* knots = a.knots + size_t(chunk) * (KC * DP);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i)
+#pragma unroll
+            for (int c = 0; c < D; ++c) dst[i][c] = __ldg(knots + phi_kk[i] * DP + c);
+    };
+    auto rows_load = [&](int xbuf) {
         const double* xsb = xs + xbuf * C::XS_DOUBLES;
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
+        for (int i = 0; i < VPT; ++i)
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                px[i][c] = xsb[phi_row[i] * DP + c];
-                pu[i][c] = knots[phi_kk[i] * DP + c];
-            }
-        }
+            for (int c = 0; c < D; ++c) px[i][c] = xsb[phi_row[i] * DP + c];
     };
-    auto phi_store = [&](int64_t it, const double (&val)[VPT]) {
-        double* dst = phib + int(it & 1) * C::PHI_DOUBLES;
+    auto phi_store = [&](int buf, const double (&val)[VPT]) {
+        double* dst = phib + buf * C::PHI_DOUBLES;
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int v = tid + i * NTHREADS;
@@ -215,26 +232,45 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
         }
     };
 
+    double pun[PREFETCH ? VPT : 1][3];  // prefetched knots (global/L2 latency off the slowest warp's path)
     load_xs(0, blockIdx.x);
     __syncthreads();  // barrier inits, log table and xs[0] visible
-    {
-        mbar_wait(&full[0], 0u);
-        phi_load(0, 0);
+#pragma unroll
+    for (int j = 0; j < AHEAD; ++j) {  // Phi of the first AHEAD chunks (nchunks >= 4: all in tile 0)
+        knots_load(j, pu);
+        rows_load(0);
         double val[VPT];
 #pragma unroll
         for (int i = 0; i < VPT; ++i) val[i] = tps_phi_fast<D>(px[i], pu[i], logtab);
-        phi_store(0, val);
+        phi_store(j, val);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&phi_full[j]);
     }
-    __syncthreads();
+    if constexpr (PREFETCH) {
+        const double* k0 = a.knots + size_t(AHEAD % nchunks) * (KC * DP);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i)
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) pun[i][cc] = __ldg(k0 + phi_kk[i] * DP + cc);
+    }
 
-    int64_t it = 0;
+    // Warps synchronise only through mbarriers: Phi(it) is produced during iteration it-AHEAD, so a warp
+    // may start the DMMAs of chunk `it` as soon as every warp has finished chunk it-AHEAD.  The SM's
+    // warp arbiter is strictly prioritised, so the slowest warp regularly runs alone; everything outside
+    // the DMMA block is therefore kept off its critical path: 32-bit ring counters instead of 64-bit
+    // div/mod, barrier probes and knot loads issued one iteration early, a relaxed counter to elect the
+    // warp that refills a W stage.
+    int s = 0;              // W stage of the current chunk, parity of its use
+    uint32_t wpar = 0;
+    int pb = 0;             // Phi buffer of the current chunk, parity of its use
+    uint32_t ppar = 0;
+    int cphi = AHEAD % nchunks;            // chunk (within its tile) whose Phi is produced this iteration
+    int cref = NSTAGE % nchunks;           // chunk that refills the stage released this iteration
+    int64_t left = total;                  // iterations still to run, including this one
+    bool okp = false, okw = false;         // early (non-blocking) probes of this iteration's barriers
     for (int64_t til = 0; til < ntl; ++til) {
         const int64_t tile = blockIdx.x + til * gridDim.x;
         const int xb = int(til & 1);
-        if (til + 1 < ntl) {
-            load_xs(xb ^ 1, tile + gridDim.x);
-            if (nchunks == 1) __syncthreads();
-        }
         // accumulators start at -[1, x] * Cpoly   (src/autoFRK.cpp:317-324)
         double acc[MT][NT][2];
         {
@@ -258,17 +294,39 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
             }
         }
 
-        for (int c = 0; c < nchunks; ++c, ++it) {
-            // stage of the NEXT chunk: its knots feed the Phi evaluation that overlaps this chunk's DMMAs
-            const bool more = (it + 1 < total);
-            if (more) mbar_wait(&full[int((it + 1) % NSTAGE)], uint32_t((it + 1) / NSTAGE) & 1u);
-            phi_load(more ? it + 1 : it, (c + 1 == nchunks) ? (xb ^ 1) : xb);
+        for (int c = 0; c < nchunks; ++c) {
+            // (1) Phi of THIS chunk complete: every warp has finished iteration it - AHEAD
+            if (!okp) mbar_wait(&phi_full[pb], ppar);
+            //     ... hence nobody reads the previous tile's rows any more: stage the next tile's
+            if (c == 0 && til + 1 < ntl) load_xs(xb ^ 1, tile + gridDim.x);
+            // (2) inputs of the Phi chunk produced in this iteration (rows from shared, knots prefetched)
+            const bool more = (left > AHEAD);
+            // without prefetch: knots of the Phi chunk produced now; with: those of the next iteration's
+            const int cknot = PREFETCH ? ((cphi + 1 == nchunks) ? 0 : cphi + 1) : cphi;
+            const double* knots_c = a.knots + size_t(cknot) * (KC * DP);
+            double pu_now[PREFETCH ? VPT : 1][3];
+            if constexpr (PREFETCH) {
+#pragma unroll
+                for (int i = 0; i < VPT; ++i)
+#pragma unroll
+                    for (int cc = 0; cc < D; ++cc) {
+                        pu_now[i][cc] = pun[i][cc];
+                        pun[i][cc] = __ldg(knots_c + phi_kk[i] * DP + cc);
+                    }
+            }
+            const double* xs_c = xs + ((c + AHEAD >= nchunks) ? (xb ^ 1) : xb) * C::XS_DOUBLES;
+            // (3) W of this chunk landed
+            if (!okw) mbar_wait(&w_full[s], wpar);
 
-            const int s = int(it % NSTAGE);
-            const double* ws = stage0 + size_t(s) * C::STAGE_DOUBLES + (wc * NT * 8) * 4 + lane;
-            const double* ph = phib + int(it & 1) * C::PHI_DOUBLES + (wr * MT * 8) * 4 + lane;
+            const double* ws = stage0 + s * C::STAGE_DOUBLES + (wc * NT * 8) * 4 + lane;
+            const double* ph = phib + pb * C::PHI_DOUBLES + (wr * MT * 8) * 4 + lane;
+            // ring positions of the next iteration
+            const int sn = (s + 1 == NSTAGE) ? 0 : s + 1;
+            const uint32_t wparn = (s + 1 == NSTAGE) ? (wpar ^ 1u) : wpar;
+            const int pbn = (pb + 1 == NPB) ? 0 : pb + 1;
+            const uint32_t pparn = (pb + 1 == NPB) ? (ppar ^ 1u) : ppar;
             double val[VPT];
-            // ---- one basic block: DMMAs of chunk `it` + Phi arithmetic of chunk `it + 1` ----
+            // ---- one basic block: DMMAs of chunk `it` + Phi arithmetic of chunk `it + AHEAD` ----
 #pragma unroll
             for (int q = 0; q < KQ; ++q) {
                 double af[MT], bf[NT];
@@ -280,19 +338,47 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884_nv(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-                if (q == 0) {
+                if (q == PHI_Q) {  // the scheduler hoists these loads as far as register pressure allows
 #pragma unroll
-                    for (int i = 0; i < VPT; ++i) val[i] = tps_phi_fast<D>(px[i], pu[i], logtab);
+                    for (int i = 0; i < VPT; ++i) {
+                        double x1[3], u1[3];
+#pragma unroll
+                        for (int cc = 0; cc < D; ++cc) {
+                            x1[cc] = xs_c[phi_row[i] * DP + cc];
+                            if constexpr (PREFETCH) u1[cc] = pu_now[i][cc];
+                            else u1[cc] = __ldg(knots_c + phi_kk[i] * DP + cc);
+                        }
+                        val[i] = tps_phi_fast<D>(x1, u1, logtab);
+                    }
+                }
+                if (q == KQ - 1) {  // probe the next iteration's barriers while the last DMMAs drain
+                    okp = mbar_test_wait(&phi_full[pbn], pparn);
+                    okw = mbar_test_wait(&w_full[sn], wparn);
                 }
             }
-            phi_store(it + 1, val);
-            __syncthreads();  // stage s and phi buffer (it&1) are free; phi(it+1) is visible
-            if (tid == 0 && it + NSTAGE < total) {
-                mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                tma_bulk_g2s(stage0 + size_t(s) * C::STAGE_DOUBLES,
-                             a.wpack + size_t((it + NSTAGE) % nchunks) * C::STAGE_DOUBLES, C::STAGE_BYTES,
-                             &full[s]);
+            // (4) hand Phi(it+AHEAD) over.  Its buffer (pb ^ 2, NPB = 4) was last read by the DMMAs of chunk
+            //     it+AHEAD-NPB, which every warp finished before (1) could pass.
+            if (more) phi_store(pb ^ AHEAD, val);
+            __syncwarp();
+            if (lane == 0) {
+                if (more) mbar_arrive(&phi_full[pb ^ AHEAD]);
+                // (5) the last warp to finish with W stage s refills it for chunk it + NSTAGE
+                if (smem_add_relaxed(&w_done[s], 1u) == uint32_t(NWARPS - 1)) {
+                    w_done[s] = 0;
+                    if (left > NSTAGE) {
+                        mbar_expect_tx(&w_full[s], C::STAGE_BYTES);
+                        tma_bulk_g2s(stage0 + s * C::STAGE_DOUBLES, a.wpack + size_t(cref) * C::STAGE_DOUBLES,
+                                     C::STAGE_BYTES, &w_full[s]);
+                    }
+                }
             }
+            s = sn;
+            wpar = wparn;
+            pb = pbn;
+            ppar = pparn;
+            cphi = (cphi + 1 == nchunks) ? 0 : cphi + 1;
+            cref = (cref + 1 == nchunks) ? 0 : cref + 1;
+            --left;
         }
 
         // store the tile, column-major (R layout)
@@ -314,7 +400,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
 
 // host-side launcher table entry --------------------------------------------------------------
 struct PredictKernelInfo {
-    int d, bm, bn, kc, nstage, dp, nthreads, stage_doubles;
+    int d, bm, bn, kc, nstage, dp, nthreads, stage_doubles, min_chunks;
     size_t smem_bytes;
     void (*launch)(const PredictArgs&, int grid, cudaStream_t);
     void (*prepare)();  // opt in to large dynamic shared memory (once)
@@ -332,7 +418,7 @@ void predict_launch(const PredictArgs& a, int grid, cudaStream_t st) {
 template <class C>
 constexpr PredictKernelInfo predict_info() {
     return PredictKernelInfo{C::D, C::BM, C::BN, C::KC, C::NSTAGE, C::DP, C::NTHREADS, C::STAGE_DOUBLES,
-                             C::SMEM_BYTES, &predict_launch<C>, &predict_prepare<C>};
+                             C::MIN_CHUNKS, C::SMEM_BYTES, &predict_launch<C>, &predict_prepare<C>};
 }
 
 // the instantiated configurations, per dimension (defined in mrts_predict_d{1,2,3}.cu)
@@ -352,6 +438,7 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
     predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 4>>(),  /* BM  64, BN 320 */                                \
     predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4>>(), /* BM  32, BN 384, 1 Phi/thread */                  \
-    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3>>()  /* BM  32, BN 512, 1 Phi/thread, 3 x 66 KB stages */
+    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3>>(), /* BM  32, BN 512, 1 Phi/thread, 3 x 66 KB stages */          \
+    predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()   /* BM  32, BN 512, 8 fat warps (32 x 64 tiles), experimental */
 
 }  // namespace frk

@@ -66,8 +66,8 @@ def cmle_from_stats(G, Cm, zz, n, TT, s=0.0, wSave=False, onlylogLike=None, K=No
     """cMLEimat (R/autoFRK.R:399-480) from the sufficient statistics; K selects the leading K x K / K x T blocks."""
     if onlylogLike is None:
         onlylogLike = not wSave
-    if on_device:
-        Kfull = int(G.shape[0])
+    if on_device:   # torch CUDA tensors holding column-major K x K / K x T blocks (flat or 2-D views)
+        Kfull = int(round(math.sqrt(G.numel())))
         K = Kfull if K is None else int(K)
         pG, pC, ldg, ldc = C.c_void_p(G.data_ptr()), C.c_void_p(Cm.data_ptr()), Kfull, Kfull
     else:
