@@ -22,6 +22,11 @@ import time
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
+if "reference" in sys.argv or os.environ.get("WORLD_SIZE", "1") == "1":
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core (set before numpy loads OpenBLAS)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -266,6 +271,8 @@ def main_gpu(args):
     # the two paths run the same kernel on the same rows
     same = bool(torch.equal(torch.from_numpy(oh_np[:1000].copy()), out[:1000].cpu()))
 
+    fit_block = fit_benchmarks(torch, dist, world, rank, basis, x, args) if not args.no_fit else None
+
     if rank == 0:
         flops = 2.0 * n2 * m * kstar                     # credited: projection only
         achieved = flops / (ms_step * 1e-3) / 1e12
@@ -301,10 +308,70 @@ def main_gpu(args):
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
         }
+        if fit_block:
+            line["fit"] = fit_block
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def fit_benchmarks(torch, dist, world, rank, basis, x, args):
+    """Secondary metric of BASELINE.json: fit wall time.
+    (i) configs[3]/[4]-shaped cMLE fit: rows_fit locations/GPU x K=500, T=100, basis evaluated on the fly (never
+        materialised), one all-reduce of [G|C|zz], replicated K x K stage;
+    (ii) configs[0]: autoFRK(Data=z, loc=s) on 2,000 random 2-D locations, default basis -- GPU vs the oracle."""
+    from autofrk_b200 import dist as D
+
+    out = {}
+    K = basis.X.shape[1]
+    T = 100
+    rows = min(x.shape[0], args.fit_rows)
+    plan = basis.plan()
+    gen = torch.Generator(device="cuda").manual_seed(11 + rank)
+    Z = torch.randn((T, rows), dtype=torch.float64, device="cuda", generator=gen).T
+    xs = x[:rows]
+    D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True)       # warm-up (workspaces, cuSOLVER handles)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t0 = time.perf_counter()
+    e0.record()
+    packed = D.predict_gram_shard(plan, xs, Z)
+    e1.record()
+    D.allreduce_stats(packed)
+    e2.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    from autofrk_b200.frk import cmle_from_stats
+    res = cmle_from_stats(packed[:K * K], packed[K * K:K * K + K * T], float(packed[-1].item()), rows * world, T,
+                          s=0.0, wSave=True, onlylogLike=False, K=K, on_device=True)
+    t2 = time.perf_counter()
+    gram_flops = rows * (K * (K + 1.0) + 2.0 * K * T + 2.0 * T)
+    out["cmle_sharded"] = {
+        "rows_per_gpu": rows, "K": K, "T": T, "predict_gram_ms": e0.elapsed_time(e1), "allreduce_ms": e1.elapsed_time(e2),
+        "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
+        "note": "predict_gram = K1 (basis on the fly, 2 GB chunks) + K4 (Gram/cross-products); credited Gram flops "
+                f"{gram_flops:.3e} per GPU"}
+    if rank == 0:
+        from autofrk_b200 import frk as GF
+        rng = np.random.default_rng(0)
+        loc = rng.random((2000, 2))
+        z = (3.0 * np.sin(4 * loc[:, 0]) * np.cos(3 * loc[:, 1]) + rng.standard_normal(2000)).reshape(-1, 1)
+        GF.autoFRK(z, loc, maxK=20)                                    # warm-up
+        t0 = time.perf_counter()
+        got = GF.autoFRK(z, loc)
+        t_gpu = time.perf_counter() - t0
+        out["autoFRK_config0"] = {"gpu_wall_s": t_gpu, "K_selected": int(got["G"].X.shape[1]),
+                                  "K_grid": [int(got["G"].Kgrid[0]), int(got["G"].Kgrid[-1]), len(got["G"].Kgrid)]}
+        if args.fit_oracle:
+            import oracle as O
+            t0 = time.perf_counter()
+            ref = O.autoFRK(z, loc)
+            out["autoFRK_config0"]["cpu_oracle_wall_s"] = time.perf_counter() - t0
+            out["autoFRK_config0"]["same_K"] = bool(ref["G"].X.shape[1] == got["G"].X.shape[1])
+    return out
 
 
 def fit_for_bench(Xu, K):
@@ -328,6 +395,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's 12.5M)")
     ap.add_argument("--e2e-rows", type=int, default=1_000_000)
+    ap.add_argument("--fit-rows", type=int, default=5_000_000, help="rows per GPU of the cMLE fit timing")
+    ap.add_argument("--no-fit", action="store_true", help="skip the secondary fit timings")
+    ap.add_argument("--fit-oracle", type=int, default=1, help="also time the CPU oracle's autoFRK at configs[0]")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

@@ -1,0 +1,54 @@
+"""Run under torchrun on N GPUs: row-sharded cMLEimat (fused predict->Gram, one all-reduce, replicated K x K
+stage) must equal the single-GPU fit of the same data.  Prints one JSON line on rank 0."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+from autofrk_b200 import dist as D
+from autofrk_b200 import mrts as G
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    d, m, K, T, n = 2, 400, 80, 6, 300_001
+    rng = np.random.default_rng(0)
+    Xu = rng.random((m, d))
+    fit = G.mrtsrcpp(Xu, G.xobs_diag_of(Xu, m), K - d - 1) if rank == 0 else None
+    fit = D.broadcast_fit(fit, src=0)                       # bit-identical eigenvectors on every rank
+    basis = G.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    plan = basis.plan()
+    g = torch.Generator(device="cuda").manual_seed(5)       # same global data on every rank, then sliced
+    x_all = torch.rand((d, n), dtype=torch.float64, device="cuda", generator=g)
+    z_all = torch.randn((T, n), dtype=torch.float64, device="cuda", generator=g)
+    r0, r1 = D.shard_rows(n, world, rank)
+    x, Z = x_all[:, r0:r1].contiguous().T, z_all[:, r0:r1].contiguous().T
+    out = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True)
+    res = {}
+    if rank == 0:
+        # single-GPU reference of the same call (world-size-independent path)
+        dist_initialized = True
+        packed = D.predict_gram_shard(plan, x_all.T, z_all.T)
+        torch.cuda.synchronize()
+        from autofrk_b200.frk import cmle_from_stats
+        ref = cmle_from_stats(packed[:K * K], packed[K * K:K * K + K * T], float(packed[-1].item()), n, T, s=0.0,
+                              wSave=True, onlylogLike=False, K=K, on_device=True)
+        rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+        res = dict(world=world, v=[out["v"], ref["v"]], dM=rel(out["M"], ref["M"]), dw=rel(out["w"], ref["w"]),
+                   dV=rel(out["V"], ref["V"]), dnll=abs(out["negloglik"] - ref["negloglik"]) / abs(ref["negloglik"]))
+        res["ok"] = bool(res["dM"] < 1e-10 and res["dw"] < 1e-10 and res["dV"] < 1e-10 and res["dnll"] < 1e-12)
+        print(json.dumps(res))
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not res["ok"]:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
