@@ -16,7 +16,7 @@
 //   * The FP64 ALU and the DMMA unit share one pipe on B200 (measured: profiles/fp64_peaks_r01.json),
 //     so kernel evaluation is pure overhead on the binding resource.  Every thread therefore
 //     evaluates the same number of Phi values for chunk c+1 INSIDE the DMMA block of chunk c (one
-//     basic block, branch-free table log for d = 2), letting the scheduler drop the Phi arithmetic
+//     basic block, branch-free table kernel for d = 2 and MUFU-seeded sqrt for d = 3), letting the scheduler drop the Phi arithmetic
 //     into the issue slots between dependent-free DMMAs instead of serialising it in front of them.
 //   * no CTA-wide barrier in the steady state: Phi is produced two chunks ahead and handed over through
 //     mbarriers, so warps drift up to a chunk apart and the pipe does not drain at chunk boundaries.
@@ -41,7 +41,7 @@ struct PredictCfg {
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
     static constexpr int PHI_DOUBLES = BM * KC;
     static constexpr int XS_DOUBLES = BM * DP;
-    static constexpr int LOGTAB_DOUBLES = (D == 2) ? 256 : 0;
+    static constexpr int LOGTAB_DOUBLES = (D == 2) ? 2 * kLogTabSize : 0;
     static constexpr int AHEAD = 2;               // Phi is produced this many chunks ahead of its DMMAs
     static constexpr int NPB = 4;                 // Phi chunk buffers (>= 2 * AHEAD)
     static constexpr int MIN_CHUNKS = 4;          // the plan pads the knot list to at least this many chunks
@@ -91,27 +91,27 @@ __device__ __forceinline__ double tps_phi(const double* __restrict__ x, const do
     }
 }
 
-// Branch-free FP64 natural log of a positive normal double (Tang-style, 128-entry table in shared
-// memory): x = 2^e m, m in [1,2); j = top 7 mantissa bits, r = m*rc_j - 1 (one FMA, |r| <= 2^-8),
-// log x = e ln2 + lc_j + log1p(r), log1p by a degree-7 Taylor polynomial (|r|^8/8 < 2^-67).
-// Absolute error ~1.2e-16 + 1.1e-16 |log x| (tools/logtest notes in DESIGN.md): on par with libm for
-// r^2 log r^2.  x == 0, subnormals, inf and nan give finite garbage / nan that the caller masks (x > 0)
-// or that is multiplied by x itself.
-__device__ __forceinline__ double log_pos_table(double x, const double2* __restrict__ tab) {
+// Branch-free d = 2 kernel value phi(x) = x log(x) / (16 pi) for x = r^2 >= 0 (Tang-style, 1024-entry table
+// in shared memory): x = 2^e m, m in [1,2); j = top 10 mantissa bits, r = m*rc_j - 1 (one FMA, |r| <= 2^-11);
+//   log(x)/(16 pi) = e ln2/(16 pi) + lcc_j + c (r - r^2/2 + r^3/3 - r^4/4),   c = 1/(16 pi)   (|c r^5/5| < 2e-19)
+// 13 FP64-pipe instructions per pair (libm log alone is ~50 pipe slots); absolute error 5.1e-18 on (0,2) against
+// 6.6e-18 for x*log(x)/(16 pi) with libm (tools/gen_log_table.py).  e*ln2 needs no hi/lo split: its
+// rounding error is multiplied by x = 2^e m, i.e. it is <= 1 ulp of phi.  x == 0 is masked; subnormal x gives a
+// value <= 1e-305 in magnitude; inf / nan propagate through the final multiplication by x.
+__device__ __forceinline__ double phi2_table(double x, const double2* __restrict__ tab) {
     const long long bits = __double_as_longlong(x);
     const int hi = int(bits >> 32);
-    const double2 tc = tab[(hi >> 13) & 0x7F];
+    const double2 tc = tab[(hi >> (20 - kLogTabBits)) & (kLogTabSize - 1)];
     const double ef = double((hi >> 20) - 1023);
     const double m = __longlong_as_double((bits & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
     const double r = fma(m, tc.x, -1.0);
-    double p = 1.0 / 7.0;
-    p = fma(p, r, -1.0 / 6.0);
-    p = fma(p, r, 0.2);
-    p = fma(p, r, -0.25);
-    p = fma(p, r, 1.0 / 3.0);
-    p = fma(p, r, -0.5);
-    const double q = fma(r * r, p, ef * 1.90821492927058770002e-10);   // + e * ln2_lo
-    return fma(ef, 6.93147180369123816490e-01, tc.y + (r + q));        // e * ln2_hi + (lc + log1p(r))
+    constexpr double c = 0x1.45f306dc9c883p-6;  // 1/(16 pi) = 0.019894367886486918
+    double p = fma(-0.25 * c, r, c / 3.0);
+    p = fma(p, r, -0.5 * c);
+    p = fma(p, r, c);
+    const double s = fma(r, p, tc.y);
+    const double L = fma(ef, 0x1.c3dc98f7e969cp-7, s);  // ln2 / (16 pi) = 0.013789725009540725
+    return (x > 0.0) ? x * L : 0.0;
 }
 
 // Branch-free FP64 sqrt of x >= 0: MUFU seed (rsqrt.approx.f64, ~2^-21), two Newton steps on 1/sqrt, one
@@ -137,9 +137,7 @@ __device__ __forceinline__ double tps_phi_fast(const double (&x)[3], const doubl
         return (r * r * r) * (1.0 / 12.0);
     } else if constexpr (D == 2) {
         const double dx = x[0] - u[0], dy = x[1] - u[1];
-        const double r2 = fma(dx, dx, dy * dy);
-        const double v = (r2 * 0.019894367886486918) * log_pos_table(r2, tab);
-        return (r2 > 0.0) ? v : 0.0;
+        return phi2_table(fma(dx, dx, dy * dy), tab);
     } else {
         const double dx = x[0] - u[0], dy = x[1] - u[1], dz = x[2] - u[2];
         return -0.125 * sqrt_pos_fast(fma(dx, dx, fma(dy, dy, dz * dz)));
@@ -197,9 +195,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
             }
     }
     if constexpr (D == 2) {
-        for (int i = tid; i < 128; i += NTHREADS) {
+        for (int i = tid; i < kLogTabSize; i += NTHREADS) {
             logtab_d[2 * i] = kLogTableDev[i].rc;
-            logtab_d[2 * i + 1] = kLogTableDev[i].lc;
+            logtab_d[2 * i + 1] = kLogTableDev[i].lcc;
         }
     }
 
@@ -454,6 +452,7 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 4>>(),  /* BM  64, BN 320 */                                \
     predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4>>(), /* BM  32, BN 384, 1 Phi/thread */                  \
     predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3>>(), /* BM  32, BN 512, 1 Phi/thread, 3 x 66 KB stages */          \
-    predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()   /* BM  32, BN 512, 8 fat warps (32 x 64 tiles), experimental */
+    predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>(),  /* BM  32, BN 512, 8 fat warps (32 x 64 tiles), experimental */ \
+    predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()   /* BM  64, BN 200, 20 thin warps, 2 Phi/thread, experimental */
 
 }  // namespace frk

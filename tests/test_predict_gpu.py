@@ -11,6 +11,9 @@ pytestmark = pytest.mark.gpu
 
 # (d, m, kstar, n2): cover every K1 slice configuration (BN 32..512, two slices), ragged rows / knots
 CASES = [
+    (2, 6, 2, 50),        # fewer knots than one chunk: the plan pads to 4 zero-weight chunks
+    (1, 5, 3, 9),
+    (3, 9, 4, 33),
     (2, 37, 4, 1),
     (2, 64, 20, 7),
     (2, 101, 28, 255),
@@ -76,6 +79,33 @@ def test_predict_mrts_basis_and_identity():
     sub = gobj.leading(40)
     refsub = O.predict_mrts(oobj.leading(40), xnew)
     assert colrel(G.predict_mrts(sub, xnew), refsub) < TOL
+
+
+def test_empty_and_degenerate_inputs():
+    from autofrk_b200 import mrts as G
+
+    d, m, kstar = 2, 40, 10
+    Xu, xd, fit, rng = make_fit(d, m, kstar, seed=3)
+    out = G.mrtsrcpp_predict(Xu, xd, np.zeros((0, d)), fit["BBBH"], fit["UZ"], fit["nconst"], kstar)
+    assert out["X1"].shape == (0, kstar)
+    # all-zero eigenvector block: X1 is identically zero, no kernel launch needed
+    UZ0 = np.zeros_like(fit["UZ"])
+    out = G.mrtsrcpp_predict(Xu, xd, rng.random((17, d)), fit["BBBH"], UZ0, fit["nconst"], kstar)
+    assert np.all(out["X1"] == 0.0)
+    # non-finite coordinates propagate as NaN / stay confined to their own rows
+    x = rng.random((64, d))
+    x[5, 0] = np.nan
+    got = G.mrtsrcpp_predict(Xu, xd, x, fit["BBBH"], fit["UZ"], fit["nconst"], kstar)["X1"]
+    assert np.all(np.isnan(got[5])) and np.all(np.isfinite(np.delete(got, 5, axis=0)))
+    # very large / very small coordinate scales (the table log and the MUFU-seeded sqrt take any normal double)
+    import oracle as O
+    for d2, scale in ((2, 1e-60), (2, 1e60), (3, 1e-100), (3, 1e100)):
+        Xs = rng.random((30, d2)) * scale
+        fit2 = O.mrtsrcpp(Xs, np.eye(d2), 6)
+        xn = rng.random((40, d2)) * scale
+        ref = O.mrtsrcpp_predict(Xs, None, xn, fit2["BBBH"], fit2["UZ"], fit2["nconst"], 6)["X1"]
+        got = G.mrtsrcpp_predict(Xs, None, xn, fit2["BBBH"], fit2["UZ"], fit2["nconst"], 6)["X1"]
+        assert colrel(got, ref) < 1e-9, (d2, scale, colrel(got, ref))
 
 
 def test_error_messages_match_reference():

@@ -8,7 +8,8 @@ code = r'''
 import sys, json, numpy as np, torch
 sys.path.insert(0, ".")
 from autofrk_b200 import mrts as G
-d, m, kstar, n2 = 2, 1000, 497, 2_000_000
+import os
+d, m, kstar, n2 = [int(v) for v in os.environ.get('FRK_PROBE_SHAPE', '2,1000,497,2000000').split(',')]
 rng = np.random.default_rng(0)
 Xu = rng.random((m, d)); UZ = np.zeros((m + d + 1, kstar + d + 1)); UZ[:m, :kstar] = rng.standard_normal((m, kstar))
 plan = G.MrtsPlan(Xu, rng.standard_normal((d + 1, m)), UZ, np.ones(d), kstar)
