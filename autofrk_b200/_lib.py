@@ -54,10 +54,10 @@ _SIGNATURES = {
     "frk_plan_launches": (_i64, [_vp]),
     "frk_plan_predict": (_i32, [_vp, _vp, _i64, _vp, _i32]),
     "frk_plan_predict_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp]),
-    "frk_gram_stats": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "frk_gram_stats": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "frk_gram_packed_len": (_i64, [_i32, _i32]),
-    "frk_gram_stats_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _vp, _vp]),
-    "frk_plan_predict_gram_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _i64, _vp]),
+    "frk_gram_stats_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "frk_plan_predict_gram_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _i64, _vp]),
     "frk_getHalf": (_i32, [_vp, _i64, _i32, _vp]),
     "frk_cMLEimat_stats": (_i32, [_vp, _i64, _vp, _i64, C.c_double, _i32, _i32, _i64, C.c_double, _i32, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _vp]),

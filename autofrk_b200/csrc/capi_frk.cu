@@ -40,7 +40,7 @@ int64_t default_chunk_rows(const frk::MrtsPlan* mp, int K) {
 }
 
 void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, const double* dZ, int T, int64_t ldz,
-                  double* dpacked, int64_t chunk_rows, cudaStream_t st) {
+                  const double* dw, double* dpacked, int64_t chunk_rows, cudaStream_t st) {
     frk::MrtsPlan* mp = plan->mp;
     const int K = mp->k;
     if (chunk_rows <= 0) chunk_rows = default_chunk_rows(mp, K);
@@ -54,8 +54,8 @@ void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, con
     for (int64_t r0 = 0; r0 < n2; r0 += chunk_rows) {
         const int64_t rows = std::min(chunk_rows, n2 - r0);
         frk::plan_predict_basis_dev(mp, dx + r0, rows, ldx, plan->fchunk.p, chunk_rows, st);
-        frk::gram_stats_dev(plan->fchunk.p, rows, K, chunk_rows, T > 0 ? dZ + r0 : nullptr, T, ldz, plan->packed_tmp.p, ws,
-                            st);
+        frk::gram_stats_dev(plan->fchunk.p, rows, K, chunk_rows, T > 0 ? dZ + r0 : nullptr, T, ldz, dw ? dw + r0 : nullptr,
+                            plan->packed_tmp.p, ws, st);
         axpy_kernel<<<unsigned((plen + 255) / 256), 256, 0, st>>>(dpacked, plan->packed_tmp.p, int64_t(plen), first);
         FRK_CUDA(cudaGetLastError());
         mp->launches += 4;
@@ -70,15 +70,15 @@ extern "C" {
 int64_t frk_gram_packed_len(int32_t K, int32_t T) { return int64_t(frk::gram_packed_len(K, T)); }
 
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
-                           int64_t ldz, double* d_packed, void* stream) {
+                           int64_t ldz, const double* d_weights, double* d_packed, void* stream) {
     return guarded([&] {
-        frk::gram_stats_dev(d_F, n, K, ldf, d_Z, T, ldz, d_packed, frk_capi::gram_workspace(),
+        frk::gram_stats_dev(d_F, n, K, ldf, d_Z, T, ldz, d_weights, d_packed, frk_capi::gram_workspace(),
                             static_cast<cudaStream_t>(stream));
     });
 }
 
-int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, double* G, double* C,
-                       double* zz) {
+int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, const double* weights,
+                       double* G, double* C, double* zz) {
     return guarded([&] {
         require_device();
         if (K < 1 || n < 1) frk::fail(FRK_EINVAL, "F must be a non-empty matrix");
@@ -87,10 +87,11 @@ int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, i
         int64_t rc = (int64_t(1) << 30) / (int64_t(K + T) * 8);
         rc = std::max<int64_t>(4096, rc / 16 * 16);
         rc = std::min(rc, (n + 1) / 2 * 2);
-        frk::DevBuf<double> dF[2], dZ[2], packed(frk::gram_packed_len(K, T)), ptmp(frk::gram_packed_len(K, T));
+        frk::DevBuf<double> dF[2], dZ[2], dW[2], packed(frk::gram_packed_len(K, T)), ptmp(frk::gram_packed_len(K, T));
         for (int b = 0; b < 2; ++b) {
             dF[b].alloc(size_t(rc) * K);
             if (T > 0) dZ[b].alloc(size_t(rc) * T);
+            if (weights) dW[b].alloc(static_cast<size_t>(rc));
         }
         cudaStream_t s_comp, s_copy;
         FRK_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
@@ -113,9 +114,12 @@ int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, i
                 if (T > 0)
                     FRK_CUDA(cudaMemcpy2DAsync(dZ[b].p, sizeof(double) * rc, Z + r0, sizeof(double) * n,
                                                sizeof(double) * rows, size_t(T), cudaMemcpyHostToDevice, s_copy));
+                if (weights)
+                    FRK_CUDA(cudaMemcpyAsync(dW[b].p, weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, s_copy));
                 FRK_CUDA(cudaEventRecord(ev_in[b], s_copy));
                 FRK_CUDA(cudaStreamWaitEvent(s_comp, ev_in[b], 0));
-                frk::gram_stats_dev(dF[b].p, rows, K, rc, T > 0 ? dZ[b].p : nullptr, T, rc, ptmp.p, ws, s_comp);
+                frk::gram_stats_dev(dF[b].p, rows, K, rc, T > 0 ? dZ[b].p : nullptr, T, rc, weights ? dW[b].p : nullptr,
+                                    ptmp.p, ws, s_comp);
                 axpy_kernel<<<unsigned((plen + 255) / 256), 256, 0, s_comp>>>(packed.p, ptmp.p, int64_t(plen), first);
                 FRK_CUDA(cudaGetLastError());
                 FRK_CUDA(cudaEventRecord(ev_done[b], s_comp));
@@ -138,12 +142,14 @@ int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, i
 }
 
 int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, const double* d_Z,
-                                  int32_t T, int64_t ldz, double* d_packed, int64_t chunk_rows, void* stream) {
+                                  int32_t T, int64_t ldz, const double* d_weights, double* d_packed,
+                                  int64_t chunk_rows, void* stream) {
     return guarded([&] {
         if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
         if (n2 < 1) frk::fail(FRK_EINVAL, "xnew must have at least one row");
         if (ldx < n2 || (T > 0 && ldz < n2)) frk::fail(FRK_EINVAL, "leading dimensions must be >= n2");
-        predict_gram(plan, d_xnew, n2, ldx, d_Z, T, ldz, d_packed, chunk_rows, static_cast<cudaStream_t>(stream));
+        predict_gram(plan, d_xnew, n2, ldx, d_Z, T, ldz, d_weights, d_packed, chunk_rows,
+                     static_cast<cudaStream_t>(stream));
     });
 }
 

@@ -2,6 +2,8 @@
 //   G = F'F      (R/helper.R:20  `t(Fk) %*% iDFk`, identity D)              K x K
 //   C = F'Z      (what R/autoFRK.R:433-435 needs: ihF %*% Data = half %*% (F'Z))   K x T
 //   zz = sum(Z^2) (R/autoFRK.R:431)
+// With optional row weights w (diagonal D^-1: cMLEsp, R/autoFRK.R:528-538; NA masks: R/autoFRK.R:609-615) the
+// same pass gives G = F' diag(w) F, C = F' diag(w) Z, zz = sum(w Z^2).
 // F is n x K, Z is n x T, both column-major (R layout), so the long dimension n is the MMA k-dimension
 // and both operands of every product are column panels of the same matrices.
 //
@@ -29,7 +31,8 @@ constexpr int SP = KR + 4;    // padded column stride in shared memory (doubles)
 constexpr int NST = 4;        // cp.async stages
 constexpr int NTHREADS = 512;
 constexpr int PANEL_DOUBLES = TB * SP;
-constexpr size_t GRAM_SMEM = size_t(NST) * 2 * PANEL_DOUBLES * sizeof(double);
+constexpr int STAGE_DOUBLES = 2 * PANEL_DOUBLES + KR;  // A panel, B panel, row weights of the stage
+constexpr size_t GRAM_SMEM = size_t(NST) * STAGE_DOUBLES * sizeof(double);
 
 struct GramArgs {
     const double* F;
@@ -39,6 +42,7 @@ struct GramArgs {
     int64_t ldz;
     int T;
     int64_t n;
+    const double* w;  // optional row weights (n): G = F' diag(w) F, C = F' diag(w) Z; nullptr = identity
     int ntf, ntz, npairs, nsplit;
     int64_t rows_per_split;
     double* partial;  // [nsplit][npairs][TB*TB], column-major tiles
@@ -56,7 +60,7 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <bool ALIGNED>
+template <bool ALIGNED, bool WEIGHTED>
 __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const smem = reinterpret_cast<double*>(smem_raw);
@@ -122,10 +126,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
         }
     };
     auto load_stage = [&](int stage, int step) {
-        double* As = smem + size_t(stage) * 2 * PANEL_DOUBLES;
+        double* As = smem + size_t(stage) * STAGE_DOUBLES;
         const int64_t r0 = r_begin + int64_t(step) * KR;
         load_panel(As, Abase, Ald, Acols, r0);
         if (!diag) load_panel(As + PANEL_DOUBLES, Bbase, Bld, Bcols, r0);
+        if (WEIGHTED && tid < KR) {  // weights of the stage's rows (0 past the split's end)
+            const int bytes = (r0 + tid < r_end) ? 8 : 0;
+            cp_async8(As + 2 * PANEL_DOUBLES + tid, bytes ? a.w + r0 + tid : a.w, bytes);
+        }
     };
 
     double acc[4][4][2];
@@ -144,8 +152,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
         __syncthreads();
         if (step + NST - 1 < nsteps) load_stage((step + NST - 1) % NST, step + NST - 1);
         cp_async_commit();
-        const double* As = smem + size_t(step % NST) * 2 * PANEL_DOUBLES;
+        const double* As = smem + size_t(step % NST) * STAGE_DOUBLES;
         const double* Bs = diag ? As : As + PANEL_DOUBLES;
+        const double* wsm = As + 2 * PANEL_DOUBLES + t;
         const double* ap = As + (wr * 32 + g) * SP + t;
         const double* bp = Bs + (wc * 32 + g) * SP + t;
 #pragma unroll
@@ -155,6 +164,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
             for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * SP + 4 * q];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) bf[nt] = bp[nt * 8 * SP + 4 * q];
+            if (WEIGHTED) {  // A operand = F' diag(w): row 4q+t of the stage
+                const double wq = wsm[4 * q];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) af[mt] *= wq;
+            }
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -177,13 +191,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
 }
 
 // sum of squares of Z (n x T, ld ldz): fixed grid, per-block partials, summed later in a fixed order
-__global__ void sumsq_kernel(const double* __restrict__ Z, int64_t ldz, int64_t n, int T, double* __restrict__ part) {
+__global__ void sumsq_kernel(const double* __restrict__ Z, int64_t ldz, int64_t n, int T, const double* __restrict__ w,
+                             double* __restrict__ part) {
     double s = 0.0;
     const int64_t total = n * int64_t(T);
     for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
         const int64_t c = idx / n, i = idx % n;
         const double z = Z[i + c * ldz];
-        s = fma(z, z, s);
+        s = fma(w ? z * w[i] : z, z, s);
     }
     __shared__ double sh[256];
     sh[threadIdx.x] = s;
@@ -244,7 +259,7 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nspli
 size_t gram_packed_len(int K, int T) { return size_t(K) * K + size_t(K) * T + 1; }
 
 void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
-                    double* dpacked, GramWorkspace& ws, cudaStream_t st) {
+                    const double* dw, double* dpacked, GramWorkspace& ws, cudaStream_t st) {
     if (K < 1) fail(1, "F must have at least one column");
     if (n < 1) fail(1, "F must have at least one row");
     if (T < 0) fail(1, "T must be non-negative");
@@ -257,6 +272,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     a.F = dF; a.ldf = ldf; a.K = K;
     a.Z = dZ; a.ldz = ldz; a.T = T;
     a.n = n;
+    a.w = dw;
     a.ntf = (K + TB - 1) / TB;
     a.ntz = (T + TB - 1) / TB;
     a.npairs = a.ntf * (a.ntf + 1) / 2 + a.ntf * a.ntz;
@@ -282,20 +298,23 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
                          (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));
     static bool attr_set = false;
     if (!attr_set) {
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
         attr_set = true;
     }
     if (T > 0) {
-        sumsq_kernel<<<nzz, 256, 0, st>>>(dZ, ldz, n, T, ws.zzpart.p);
+        sumsq_kernel<<<nzz, 256, 0, st>>>(dZ, ldz, n, T, dw, ws.zzpart.p);
     } else {
         FRK_CUDA(cudaMemsetAsync(ws.zzpart.p, 0, sizeof(double) * nzz, st));
     }
     FRK_CUDA(cudaGetLastError());
-    if (aligned)
-        gram_kernel<true><<<a.nsplit * a.npairs, NTHREADS, GRAM_SMEM, st>>>(a);
-    else
-        gram_kernel<false><<<a.nsplit * a.npairs, NTHREADS, GRAM_SMEM, st>>>(a);
+    const int grid = a.nsplit * a.npairs;
+    if (aligned && !dw) gram_kernel<true, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+    else if (!aligned && !dw) gram_kernel<false, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+    else if (aligned) gram_kernel<true, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+    else gram_kernel<false, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
     FRK_CUDA(cudaGetLastError());
     gram_reduce_kernel<<<a.npairs, 256, 0, st>>>(ws.partial.p, a.nsplit, a.npairs, a.ntf, a.ntz, K, T, ws.zzpart.p, nzz,
                                                  dpacked);

@@ -15,7 +15,8 @@ struct GramWorkspace {
 size_t gram_packed_len(int K, int T);
 
 // dF n x K (ld ldf), dZ n x T (ld ldz; T may be 0) on the device -> dpacked on the device; asynchronous on st.
+// dw: optional row weights (n doubles, device) or nullptr.
 void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
-                    double* dpacked, GramWorkspace& ws, cudaStream_t st);
+                    const double* dw, double* dpacked, GramWorkspace& ws, cudaStream_t st);
 
 }  // namespace frk

@@ -78,7 +78,7 @@ def broadcast_fit(fit: dict | None, src: int = 0) -> dict:
     return out
 
 
-def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0):
+def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0, w_t=None):
     """packed statistics of this rank's rows, basis never materialised (frk_plan_predict_gram_dev)."""
     import torch
 
@@ -91,6 +91,7 @@ def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0):
     st = C.c_void_p(torch.cuda.current_stream(x_t.device).cuda_stream)
     check(lib.frk_plan_predict_gram_dev(plan._h, C.c_void_p(x_t.data_ptr()), n2, ldx,
                                         C.c_void_p(Z_t.data_ptr()) if T else None, T, ldz,
+                                        None if w_t is None else C.c_void_p(w_t.data_ptr()),
                                         C.c_void_p(packed.data_ptr()), int(chunk_rows), st))
     return packed
 

@@ -23,10 +23,13 @@ from ._lib import check, fmat, lib, ptr
 from .mrts import MrtsBasis, getASCeigens, mrts, predict_mrts
 
 
-def gram_stats(Fk, Data=None):
-    """(G, C, zz) = (F'F, F'Z, sum(Z^2)) in one device pass over the rows."""
+def gram_stats(Fk, Data=None, weights=None):
+    """(G, C, zz) = (F'WF, F'WZ, sum(w Z^2)) in one device pass over the rows (W = diag(weights), default I)."""
     F = fmat(Fk, "Fk")
     n, K = F.shape
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64).ravel()
+    if w is not None and w.size != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "weights must have one entry per row of Fk")
     Z = None if Data is None else fmat(Data, "Data")
     T = 0 if Z is None else Z.shape[1]
     if Z is not None and Z.shape[0] != n:
@@ -34,7 +37,8 @@ def gram_stats(Fk, Data=None):
     G = np.empty((K, K), order="F")
     Cm = np.empty((K, max(T, 1)), order="F")
     zz = C.c_double(0.0)
-    check(lib.frk_gram_stats(ptr(F), n, K, None if Z is None else ptr(Z), T, ptr(G), ptr(Cm), C.byref(zz)))
+    check(lib.frk_gram_stats(ptr(F), n, K, None if Z is None else ptr(Z), T, None if w is None else ptr(w), ptr(G),
+                             ptr(Cm), C.byref(zz)))
     return G, (Cm if T else None), zz.value
 
 
@@ -101,6 +105,30 @@ def cMLEimat(Fk, Data, s, wSave=False, S=None, onlylogLike=None):
     return cmle_from_stats(G, Cm, zz, F.shape[0], Z.shape[1], s=s, wSave=wSave, onlylogLike=onlylogLike)
 
 
+def cMLEsp(Fk, Data, Depsilon, wSave=False):
+    """R/autoFRK.R:528-558 for a DIAGONAL Depsilon (vector of its diagonal, or a diagonal matrix).
+
+    iD enters only through the weighted statistics G = F' iD F, C = F' iD Z, zz = sum(iD Z^2) (one weighted
+    device pass); with half G half = I the wSave products collapse to the same closed forms as cMLEimat."""
+    De = np.asarray(Depsilon, dtype=np.float64)
+    if De.ndim == 2:
+        if np.count_nonzero(De - np.diag(np.diag(De))):
+            raise NotImplementedError("non-diagonal Depsilon needs spam's sparse solve, out of scope (SURVEY.md 2 #19)")
+        De = np.diag(De)
+    F, Z = fmat(Fk, "Fk"), fmat(Data, "Data")
+    if De.size != F.shape[0]:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "Depsilon must be n x n")
+    iD = 1.0 / De                                               # :530
+    ldetD = float(np.sum(np.log(De)))                           # :531
+    G, Cm, zz = gram_stats(F, Z, weights=iD)                    # :532-538 in one weighted pass
+    TT = Z.shape[1]
+    out = cmle_from_stats(G, Cm, zz, F.shape[0], TT, s=0.0, wSave=wSave)   # :539-552
+    out["negloglik"] = out["negloglik"] + ldetD * TT            # ldet * TT, R/autoFRK.R:379-380,393-396
+    if "v" in out:
+        out["s"] = out.pop("v")                                 # :554-555
+    return out
+
+
 def cMLE(Fk, TT, trS, half, JSJ=None, s=0.0, ldet=None, wSave=False, onlylogLike=None, vfixed=None):
     """R/autoFRK.R:333-397."""
     if onlylogLike is None:
@@ -134,8 +162,16 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
 
     The AIC sweep uses ONE max-K pass over the rows: every candidate K works on the leading K columns of
     Fk, i.e. on the leading principal blocks of G = F'F and C = F'Z (R recomputes both for each K)."""
-    if D is not None or DfromLK is not None:
-        raise NotImplementedError("non-identity D / LatticeKrig (cMLEsp, cMLElk) is out of scope (SURVEY.md 2 #19-20)")
+    if DfromLK is not None:
+        raise NotImplementedError("LatticeKrig fine scale (cMLElk) is out of scope (SURVEY.md 2 #20)")
+    iD = None
+    if D is not None:                                           # diagonal D: iD = solve(D) as row weights (:289-291)
+        Dd = np.asarray(D, dtype=np.float64)
+        if Dd.ndim == 2:
+            if np.count_nonzero(Dd - np.diag(np.diag(Dd))):
+                raise NotImplementedError("non-diagonal D needs spam's sparse solve, out of scope (SURVEY.md 2 #19)")
+            Dd = np.diag(Dd)
+        iD = 1.0 / Dd
     if method != "fast":
         raise NotImplementedError('method="EM" (EM0miss) is out of scope (SURVEY.md 2 #21)')
     Z = fmat(Data, "Data")
@@ -167,7 +203,7 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
     if Fk is None:
         Fk = mrts(knot, int(K.max()), loc, maxknot)             # :260
     TT = Z.shape[1]
-    G, Cm, zz = gram_stats(Fk.X, Z)                             # one pass; trS = zz/TT (:304)
+    G, Cm, zz = gram_stats(Fk.X, Z, weights=iD)                 # one pass; trS = zz/TT (:304)
     AIC = np.full(K.size, np.inf)
     for i, k in enumerate(K):                                   # :305-317
         AIC[i] = cmle_from_stats(G, Cm, zz, N, TT, s=0.0, wSave=False, onlylogLike=True, K=int(k))["negloglik"]
@@ -180,13 +216,25 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
 
 
 def indeMLE(Data, Fk, D=None, maxit=50, avgtol=1e-6, wSave=False, DfromLK=None, vfixed=None, sigma_FRK=None):
-    """R/autoFRK.R:739-843, the isimat / complete-data branch (:778-803)."""
-    if D is not None or DfromLK is not None:
-        raise NotImplementedError("non-identity D / LatticeKrig (cMLEsp, cMLElk) is out of scope (SURVEY.md 2 #19-20)")
+    """R/autoFRK.R:739-843, complete data: isimat -> cMLEimat (:778-803), other diagonal D -> cMLEsp (:805-813)."""
+    if DfromLK is not None:
+        raise NotImplementedError("LatticeKrig fine scale (cMLElk) is out of scope (SURVEY.md 2 #20)")
     Z = fmat(Data, "Data")
     if np.isnan(Z).any():
         raise NotImplementedError("missing values (EM0miss) are out of scope (SURVEY.md 2 #21)")
     F = Fk.X if isinstance(Fk, MrtsBasis) else fmat(Fk, "Fk")
+    if D is not None:
+        Dd = np.asarray(D, dtype=np.float64)
+        if Dd.ndim == 2:
+            if np.count_nonzero(Dd - np.diag(np.diag(Dd))):
+                raise NotImplementedError("non-diagonal D needs spam's sparse solve, out of scope (SURVEY.md 2 #19)")
+            Dd = np.diag(Dd)
+        # isimat: checkDiag(D) and a constant diagonal (R/autoFRK.R:775-776) -- the constant itself is ignored there
+        if np.sum(np.abs(np.mean(Dd) - Dd)) >= np.finfo(float).eps:
+            out = cMLEsp(F, Z, Dd, wSave)                       # :806
+            if wSave:
+                out["pinfo"] = {"D": Dd, "pick": np.arange(Z.shape[0])}   # :811
+            return out
     sigma = 0.0 if sigma_FRK is None else float(sigma_FRK)      # options(sigma_FRK) :779-783
     out = cMLEimat(F, Z, s=sigma, wSave=wSave)                  # :787
     if "v" in out:                                              # :788-795

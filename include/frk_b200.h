@@ -106,19 +106,23 @@ int32_t frk_plan_predict_dev(frk_plan* plan, const double* d_xnew, int64_t n2, i
 /* Sufficient statistics of the fit in one pass over the rows:
  *   G = F'F (K x K; replaces `t(Fk) %*% iDFk`, R/helper.R:20), C = F'Z (K x T; all that
  *   R/autoFRK.R:433-435 needs because ihF %*% Data == half %*% (F'Z)), zz = sum(Z^2) (R/autoFRK.R:431).
- * F is n x K, Z is n x T (T may be 0, then Z, C may be NULL), host pointers, column-major. */
-int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, double* G, double* C,
-                       double* zz);
+ * F is n x K, Z is n x T (T may be 0, then Z, C may be NULL), host pointers, column-major.
+ * `weights` (n, may be NULL): row weights w_i, giving G = F' diag(w) F, C = F' diag(w) Z, zz = sum(w Z^2) -- the
+ * diagonal-D statistics `t(Fk) %*% iD %*% Fk` etc. of cMLEsp (R/autoFRK.R:528-538) and, with 0/1 weights, the
+ * per-replicate NA-masked Grams of EM0miss (R/autoFRK.R:609-615). */
+int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, int32_t T, const double* weights,
+                       double* G, double* C, double* zz);
 /* length of the packed device result [G (K*K) | C (K*T) | zz (1)] */
 int64_t frk_gram_packed_len(int32_t K, int32_t T);
 /* device pointers: F n x K (ld ldf), Z n x T (ld ldz) -> d_packed; asynchronous on `stream`.
  * Multi-GPU: every rank calls this on its row shard, then one allreduce(sum) of d_packed. */
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
-                           int64_t ldz, double* d_packed, void* stream);
+                           int64_t ldz, const double* d_weights, double* d_packed, void* stream);
 /* fused predict.mrts -> Gram: the n2 x K basis is produced chunk by chunk (chunk_rows rows, 0 = default)
  * and reduced at once, so it is never materialised.  d_Z is n2 x T (ld ldz). */
 int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, const double* d_Z,
-                                  int32_t T, int64_t ldz, double* d_packed, int64_t chunk_rows, void* stream);
+                                  int32_t T, int64_t ldz, const double* d_weights, double* d_packed,
+                                  int64_t chunk_rows, void* stream);
 
 /* getHalf (R/helper.R:19-26) given G = t(Fk) %*% iDFk (K x K, ld ldg, lower triangle read): half = G^(-1/2),
  * zero eigenvalues -> 0. */

@@ -184,6 +184,39 @@ def cMLEimat(Fk, Data, s, wSave=False, S=None, onlylogLike=None):
     return {"v": v, "M": M, "s": s, "negloglik": nll, "w": etatt, "V": V}
 
 
+def cMLEsp(Fk, Data, Ddiag, wSave=False):
+    """R/autoFRK.R:528-558 for a DIAGONAL Depsilon given by its diagonal `Ddiag` (the literal n-sized products)."""
+    Fk = np.asarray(Fk, dtype=np.float64)
+    Data = _as2d(Data)
+    Dd = np.asarray(Ddiag, dtype=np.float64).ravel()
+    iD = 1.0 / Dd                                              # :530
+    ldetD = float(np.sum(np.log(Dd)))                          # :531
+    iDFk = iD[:, None] * Fk                                    # :532
+    half = getHalf(Fk, iDFk)                                   # :533
+    ihFiD = half @ iDFk.T                                      # :534
+    TT = Data.shape[1]
+    t = ihFiD @ Data
+    JSJ = (t @ t.T) / TT                                       # :536
+    JSJ = (JSJ + JSJ.T) / 2                                    # :537
+    trS = np.sum(np.sum((iD[:, None] * Data) * Data, axis=1)) / TT   # :538
+    out = cMLE(Fk, TT, trS, half, JSJ, s=0.0, ldet=ldetD, wSave=wSave)  # :539
+    if wSave:
+        L = out["L"]                                           # :541
+        invD = iD / (out["s"] + out["v"])                      # :542
+        iDZ = invD[:, None] * Data                             # :543
+        KL = L.shape[1]
+        right0 = L @ np.linalg.inv(np.eye(KL) + L.T @ (invD[:, None] * L))      # :544-545
+        INVtZ = iDZ - invD[:, None] * (right0 @ (L.T @ iDZ))   # :546
+        out["w"] = out["M"] @ Fk.T @ INVtZ                     # :547-548
+        GM = Fk @ out["M"]                                     # :549
+        iDGM = invD[:, None] * GM                              # :550
+        out["V"] = out["M"] - GM.T @ (iDGM - invD[:, None] * (right0 @ (L.T @ iDGM)))  # :551-552
+    out["s"] = out.get("v")                                    # :554
+    out.pop("v", None)                                         # :555
+    out.pop("L", None)                                         # :556
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # (G, C, zz) restatement -- what the CUDA path evaluates (SURVEY.md 8(a) a11-a13)
 # --------------------------------------------------------------------------------------------

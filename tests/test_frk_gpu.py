@@ -59,7 +59,7 @@ def test_gram_dev_and_fused_predict_gram():
     for r0, r1 in ((0, 20_000), (20_000, n)):
         part = torch.empty(plen, dtype=torch.float64, device="cuda")
         _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F[r0:].data_ptr()), r1 - r0, K, n, C.c_void_p(Z[r0:].data_ptr()),
-                                               T, n, C.c_void_p(part.data_ptr()), st))
+                                               T, n, None, C.c_void_p(part.data_ptr()), st))
         packed += part
     torch.cuda.synchronize()
     Fh, Zh = F.cpu().numpy(), Z.cpu().numpy()
@@ -69,7 +69,7 @@ def test_gram_dev_and_fused_predict_gram():
     assert abs(packed[-1].item() - np.sum(Zh * Zh)) / np.sum(Zh * Zh) < 1e-13
     # (2) fused: chunks of 8192 rows, basis never stored
     fused = torch.empty(plen, dtype=torch.float64, device="cuda")
-    _lib.check(_lib.lib.frk_plan_predict_gram_dev(plan._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(Z.data_ptr()), T, n,
+    _lib.check(_lib.lib.frk_plan_predict_gram_dev(plan._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(Z.data_ptr()), T, n, None,
                                                   C.c_void_p(fused.data_ptr()), 8192, st))
     torch.cuda.synchronize()
     assert relmax(fused.cpu().numpy(), packed.cpu().numpy()) < 1e-12
@@ -204,3 +204,35 @@ def test_autoFRK_multi_replicate_with_given_basis():
     B = O.predict_mrts(Fo, newloc)
     se_closed = np.sqrt(np.maximum(0, np.sum((B @ closed["V"]) * B, axis=1)))
     assert relmax(pg["se"][:, 0], se_closed) < 1e-8
+
+
+def test_weighted_gram_and_cMLEsp_diagonal_D():
+    """row-weighted reductions (G = F' iD F, ...) and the diagonal-D fit cMLEsp (R/autoFRK.R:528-558)."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    n, K, T = 9001, 37, 4
+    F, Z = _data(n, K, T, seed=21)
+    rng = np.random.default_rng(5)
+    w = rng.random(n) + 0.25
+    Gm, Cm, zz = G.gram_stats(F, Z, weights=w)
+    assert relmax(Gm, F.T @ (w[:, None] * F)) < 1e-12
+    assert relmax(Cm, F.T @ (w[:, None] * Z)) < 1e-12
+    assert abs(zz - np.sum(w[:, None] * Z * Z)) / zz < 1e-13
+    mask = (rng.random(n) > 0.3).astype(float)             # 0/1 weights = NA mask of one replicate (R/autoFRK.R:609-615)
+    Gk, Ck, _ = G.gram_stats(F, Z[:, :1], weights=mask)
+    o = mask > 0
+    assert relmax(Gk, F[o].T @ F[o]) < 1e-12 and relmax(Ck, F[o].T @ Z[o, :1]) < 1e-12
+    D = 1.0 / w
+    ref = O.cMLEsp(F, Z, D, wSave=True)
+    got = G.cMLEsp(F, Z, D, wSave=True)
+    assert abs(got["s"] - ref["s"]) <= TOL * abs(ref["s"])
+    assert abs(got["negloglik"] - ref["negloglik"]) <= TOL * abs(ref["negloglik"])
+    assert relmax(got["M"], ref["M"]) < TOL
+    assert relmax(got["w"], ref["w"]) < 1e-9
+    assert relmax(got["V"], ref["V"]) < 1e-3                # literal V: catastrophic cancellation (SURVEY 8c (3))
+    # indeMLE routes a non-constant diagonal D to cMLEsp and a constant one to cMLEimat (R/autoFRK.R:775-806)
+    r1 = G.indeMLE(Z, F, D=D, wSave=True)
+    assert relmax(r1["M"], ref["M"]) < TOL
+    r2, r3 = G.indeMLE(Z, F, D=np.full(n, 2.0), wSave=True), G.indeMLE(Z, F, wSave=True)
+    assert np.array_equal(r2["M"], r3["M"])

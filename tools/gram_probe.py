@@ -17,7 +17,7 @@ def run(n, K, T, reps=3):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def go():
-        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, n, C.c_void_p(Z.data_ptr()), T, n,
+        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, n, C.c_void_p(Z.data_ptr()), T, n, None,
                                                C.c_void_p(packed.data_ptr()), st))
     go()
     torch.cuda.synchronize()
