@@ -148,6 +148,58 @@ def cMLE(Fk, TT, trS, half, JSJ=None, s=0.0, ldet=None, wSave=False, onlylogLike
     return {"v": v.value, "M": M, "s": s, "negloglik": nll.value, "L": None if L is None else L[:, :nL.value]}
 
 
+def _diag_of(R, n, what):
+    """diagonal of a diagonal matrix given as scalar, vector or (diagonal) matrix."""
+    R = np.asarray(R, dtype=np.float64)
+    if R.ndim == 0:
+        return np.full(n, float(R))
+    if R.ndim == 2:
+        if np.count_nonzero(R - np.diag(np.diag(R))):
+            raise NotImplementedError(f"non-diagonal {what} needs spam's sparse solve, out of scope (SURVEY.md 2 #19)")
+        R = np.diag(R)
+    if R.size != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, f"{what} must be n x n")
+    return np.ascontiguousarray(R)
+
+
+def invCz(R, L, z):
+    """R/autoFRK.R:845-852: (R + L L')^{-1} z by Woodbury, R diagonal.  The two Grams t(L) iR L and t(L) iR z are one
+    row-weighted device pass; the result is produced chunk by chunk on the device."""
+    Lm = fmat(L, "L")
+    zm = fmat(z, "z")
+    n, K = Lm.shape
+    if zm.shape[0] != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "z must have as many rows as L")
+    Rd = _diag_of(R, n, "R")
+    out = np.empty((n, zm.shape[1]), order="F")
+    check(lib.frk_invCz(ptr(Rd), ptr(Lm), ptr(zm), n, K, zm.shape[1], ptr(out)))
+    return out
+
+
+def ZinvC(R, L, z):
+    """R/helper.R:249-256 (dead code upstream): z (R + L L')^{-1} for a row-matrix z; the transpose of invCz."""
+    zm = np.atleast_2d(np.asarray(z, dtype=np.float64))
+    return np.ascontiguousarray(invCz(R, L, zm.T).T)
+
+
+def getLikelihood(Data, Fk, M, s, Depsilon):
+    """R/helper.R:28-58, diagonal Depsilon: -2 log-likelihood with per-replicate NA masks.  Every replicate's
+    masked t(L_t) R_t^-1 L_t and t(L_t) R_t^-1 z_t come from one pass over the rows of Fk with 0/1-over-R weights."""
+    Z = fmat(Data, "Data")
+    F = fmat(Fk.X if isinstance(Fk, MrtsBasis) else Fk, "Fk")
+    n, K = F.shape
+    if Z.shape[0] != n:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "Data must have as many rows as Fk")
+    O = np.asfortranarray(~np.isnan(Z), dtype=np.uint8)                       # :36
+    Z0 = np.asfortranarray(np.where(np.isnan(Z), 0.0, Z))
+    Dd = _diag_of(Depsilon, n, "Depsilon")
+    Mm = fmat(M, "M")
+    out = C.c_double(0.0)
+    check(lib.frk_getLikelihood(ptr(Z0), O.ctypes.data_as(C.c_void_p), ptr(F), ptr(Mm), float(s), ptr(Dd), n, K, Z.shape[1],
+                                C.byref(out)))
+    return out.value
+
+
 def kgrid(d, maxK):
     """Default K sequence, R/autoFRK.R:254-257."""
     K = np.unique(np.round(np.arange(d + 1, maxK + 1e-9, maxK ** (1.0 / 3) * d))).astype(int)

@@ -148,6 +148,15 @@ int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS,
 int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, const double* w, int32_t T,
                              const double* V, double* yhat, double* se);
 
+/* invCz (R/autoFRK.R:845-852): out = (R + L L')^{-1} z for a DIAGONAL R given by its diagonal Rdiag (n);
+ * L is n x K, z and out are n x T (host, column-major).  ZinvC (R/helper.R:249-256) is its transpose. */
+int32_t frk_invCz(const double* Rdiag, const double* L, const double* z, int64_t n, int32_t K, int32_t T, double* out);
+
+/* getLikelihood (R/helper.R:28-58) for a DIAGONAL Depsilon (Ddiag, n): -2 log-likelihood of Data given Fk, M, s.
+ * Data0 is Data with its NAs replaced by 0 and `observed` (n x T bytes, column-major) is !is.na(Data). */
+int32_t frk_getLikelihood(const double* Data0, const uint8_t* observed, const double* Fk, const double* M, double s,
+                          const double* Ddiag, int64_t n, int32_t K, int32_t T, double* n2loglik);
+
 /* the same two products for a basis matrix the caller already holds (predict.FRK with `basis=` or with
  * newloc = NULL, where R uses object$G): F is n x K, host, column-major; streamed through the device. */
 int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,

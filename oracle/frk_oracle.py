@@ -280,7 +280,7 @@ def getLikelihood(Data, Fk, M, s, Depsilon_diag):
         Rt = Rdiag[o]
         Lt = L[o, :]
         if Lt.shape[0] == 1:                                   # :48-51 (NCOL(Lt)==1 after drop)
-            n2loglik += math.log(Rt[0] + float(Lt @ Lt.T))
+            n2loglik += math.log(Rt[0] + float((Lt @ Lt.T)[0, 0]))
         else:
             sign, ld = np.linalg.slogdet(np.eye(K) + Lt.T @ (Lt / Rt[:, None]))
             n2loglik += ld + np.sum(np.log(Rt)) + float(np.sum(zt * invCz(Rt, Lt, zt).ravel()))  # :53-54

@@ -236,3 +236,35 @@ def test_weighted_gram_and_cMLEsp_diagonal_D():
     assert relmax(r1["M"], ref["M"]) < TOL
     r2, r3 = G.indeMLE(Z, F, D=np.full(n, 2.0), wSave=True), G.indeMLE(Z, F, wSave=True)
     assert np.array_equal(r2["M"], r3["M"])
+
+
+def test_invCz_ZinvC_getLikelihood():
+    """the Woodbury helpers named in the north star, against the oracle and against dense solves."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(17)
+    n, K, T = 6001, 14, 3
+    L = rng.standard_normal((n, K))
+    z = rng.standard_normal((n, T))
+    Rd = rng.random(n) + 0.5
+    got = G.invCz(Rd, L, z)
+    assert relmax(got, O.invCz(Rd, L, z)) < TOL
+    small = slice(0, 300)
+    dense = np.linalg.solve(np.diag(Rd[small]) + L[small] @ L[small].T, z[small])
+    assert relmax(G.invCz(Rd[small], L[small], z[small]), dense) < TOL
+    assert relmax(G.invCz(0.7, L, z[:, :1]), O.invCz(np.full(n, 0.7), L, z[:, :1])) < TOL      # scalar R = s * I
+    assert relmax(G.ZinvC(Rd[small], L[small], z[small].T), O.ZinvC(np.diag(Rd[small]), L[small], z[small].T)) < TOL
+    # getLikelihood: complete data equals cMLEimat's negloglik; with NAs equals the oracle's masked evaluation
+    F, Z = _data(4000, 9, 4, seed=3)
+    fit = O.cMLEimat(F, Z, 0.0, wSave=True)
+    ll = G.getLikelihood(Z, F, fit["M"], fit["v"], np.ones(4000))
+    assert abs(ll - fit["negloglik"]) <= 1e-9 * abs(fit["negloglik"])
+    Zna = Z.copy()
+    Zna[rng.random(Z.shape) < 0.2] = np.nan
+    Zna[:, 3] = np.nan
+    Zna[7, 3] = Z[7, 3]                                         # a replicate with ONE observation: R/helper.R:48-51 quirk
+    Dd = rng.random(4000) + 0.5
+    ref = O.getLikelihood(Zna, F, fit["M"], fit["v"], Dd)
+    got = G.getLikelihood(Zna, F, fit["M"], fit["v"], Dd)
+    assert abs(got - ref) <= 1e-9 * abs(ref), (got, ref)
