@@ -66,6 +66,8 @@ _SIGNATURES = {
     "frk_plan_predict_frk": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "frk_invCz": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "frk_getLikelihood": (_i32, [_vp, _vp, _vp, _vp, C.c_double, _vp, _i64, _i32, _i32, _vp]),
+    "frk_krige_from_stats": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "frk_plan_predict_gram": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "frk_basis_predict_frk": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -225,4 +225,83 @@ int32_t frk_getLikelihood(const double* Data0, const uint8_t* observed, const do
     });
 }
 
+int32_t frk_krige_from_stats(const double* Gg, const double* c, int32_t Tc, const double* M, int32_t K, int32_t want_V,
+                             double* coef, double* V) {
+    return guarded([&] {
+        require_device();
+        if (K < 1 || Tc < 1) frk::fail(FRK_EINVAL, "krige_from_stats: K and the number of data columns must be positive");
+        frk::LinalgHandles& lh = frk::linalg_handles();
+        cudaStream_t st = nullptr;
+        FRK_CUBLAS(cublasSetStream(lh.blas, st));
+        const double one = 1.0, zero = 0.0, mone = -1.0;
+        const int NR = Tc + (want_V ? K : 0);  // right-hand sides: [c | Gg M]
+        frk::DevBuf<double> dG(size_t(K) * K), dM(size_t(K) * K), dU(size_t(K) * K), dlam(static_cast<size_t>(K)), dA(size_t(K) * K),
+            dGA(size_t(K) * K), dS(size_t(K) * K), dR(size_t(K) * NR), dY(size_t(K) * NR), dT(size_t(K) * NR);
+        FRK_CUDA(cudaMemcpy(dG.p, Gg, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemcpy(dM.p, M, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemcpy(dR.p, c, sizeof(double) * K * Tc, cudaMemcpyHostToDevice));
+        if (want_V)  // Gg M
+            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, K, K, &one, dG.p, K, dM.p, K, &zero, dR.p + size_t(K) * Tc, K));
+        // dec <- eigen(M); A = vector %*% diag(sqrt(pmax(value, 0)))          R/autoFRK.R:1260-1264
+        FRK_CUDA(cudaMemcpy(dU.p, dM.p, sizeof(double) * K * K, cudaMemcpyDeviceToDevice));
+        frk::sym_eigen_dev(dU.p, K, dlam.p);
+        std::vector<double> lam(K), hU(size_t(K) * K);
+        FRK_CUDA(cudaMemcpy(lam.data(), dlam.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+        FRK_CUDA(cudaMemcpy(hU.data(), dU.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < K; ++j) {
+            const double sq = std::sqrt(std::fmax(lam[j], 0.0));
+            for (int i = 0; i < K; ++i) hU[i + size_t(j) * K] *= sq;
+        }
+        FRK_CUDA(cudaMemcpy(dA.p, hU.data(), sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        // S = I + A' Gg A  (= diag(1, K) + t(L) iR L, R/autoFRK.R:849);   Y = S^-1 A' [c | Gg M]
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, K, K, &one, dG.p, K, dA.p, K, &zero, dGA.p, K));
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_T, CUBLAS_OP_N, K, K, K, &one, dA.p, K, dGA.p, K, &zero, dS.p, K));
+        add_identity_kernel<<<(K + 127) / 128, 128, 0, st>>>(dS.p, K);
+        FRK_CUDA(cudaGetLastError());
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_T, CUBLAS_OP_N, K, NR, K, &one, dA.p, K, dR.p, K, &zero, dY.p, K));
+        chol_solve_logdet(dS.p, K, dY.p, NR);
+        // T = [c | Gg M] - Gg A Y ;   [coef | M - V] = M T
+        FRK_CUDA(cudaMemcpy(dT.p, dR.p, sizeof(double) * K * NR, cudaMemcpyDeviceToDevice));
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, NR, K, &mone, dGA.p, K, dY.p, K, &one, dT.p, K));
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, NR, K, &one, dM.p, K, dT.p, K, &zero, dY.p, K));
+        FRK_CUDA(cudaMemcpy(coef, dY.p, sizeof(double) * K * Tc, cudaMemcpyDeviceToHost));
+        if (want_V && V) {
+            std::vector<double> hMV(size_t(K) * K), hM(size_t(K) * K);
+            FRK_CUDA(cudaMemcpy(hMV.data(), dY.p + size_t(K) * Tc, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+            FRK_CUDA(cudaMemcpy(hM.data(), dM.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < size_t(K) * K; ++i) V[i] = hM[i] - hMV[i];   // V <- M - t(GM) %*% invCz(...)  :1270
+        }
+    });
+}
+
+int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, const double* Z, int32_t T,
+                              const double* weights, double* G, double* C, double* zz) {
+    return guarded([&] {
+        if (!plan || !plan->mp) frk::fail(FRK_EINVAL, "plan must not be NULL");
+        if (n2 < 1) frk::fail(FRK_EINVAL, "xnew must have at least one row");
+        frk::MrtsPlan* mp = plan->mp;
+        const int K = mp->k, d = mp->d;
+        const int64_t ld = (n2 + 1) / 2 * 2;  // even leading dimension: every chunk stays 16-byte aligned
+        frk::DevBuf<double> dx(size_t(ld) * d), dZ, dw, packed(frk::gram_packed_len(K, T));
+        FRK_CUDA(cudaMemcpy2D(dx.p, sizeof(double) * ld, xnew, sizeof(double) * n2, sizeof(double) * n2, size_t(d),
+                              cudaMemcpyHostToDevice));
+        if (T > 0) {
+            dZ.alloc(size_t(ld) * T);
+            FRK_CUDA(cudaMemcpy2D(dZ.p, sizeof(double) * ld, Z, sizeof(double) * n2, sizeof(double) * n2, size_t(T),
+                                  cudaMemcpyHostToDevice));
+        }
+        if (weights) {
+            dw.alloc(static_cast<size_t>(ld));
+            FRK_CUDA(cudaMemcpy(dw.p, weights, sizeof(double) * n2, cudaMemcpyHostToDevice));
+        }
+        int32_t rc = frk_plan_predict_gram_dev(plan, dx.p, n2, ld, T > 0 ? dZ.p : nullptr, T, ld, weights ? dw.p : nullptr,
+                                               packed.p, 0, nullptr);
+        if (rc != FRK_OK) frk::fail(rc, "%s", frk_last_error());
+        FRK_CUDA(cudaDeviceSynchronize());
+        FRK_CUDA(cudaMemcpy(G, packed.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
+        if (T > 0 && C) FRK_CUDA(cudaMemcpy(C, packed.p + size_t(K) * K, sizeof(double) * K * T, cudaMemcpyDeviceToHost));
+        if (zz) FRK_CUDA(cudaMemcpy(zz, packed.p + size_t(K) * K + size_t(K) * T, sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
 }  // extern "C"

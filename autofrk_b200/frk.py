@@ -208,6 +208,45 @@ def kgrid(d, maxK):
     return K
 
 
+def _krige_new_observations(obj, obsData, obsloc, mu_obs, se_report):
+    """predict.FRK with obsData (R/autoFRK.R:1197-1202, 1248-1274): replaces object$w (and V) by the kriging
+    coefficients for the new observations.  Everything n-sized is a row-weighted Gram pass over the basis at the
+    observation sites (fused with its evaluation when obsloc is given); the rest is K x K."""
+    G = obj["G"]
+    Gmat = G.X if isinstance(G, MrtsBasis) else fmat(G, "G")
+    nobs = Gmat.shape[0] if obsloc is None else fmat(obsloc, "obsloc").shape[0]
+    z = np.asarray(obsData, dtype=np.float64).reshape(-1, 1) - mu_obs           # :1198
+    if z.size != nobs:
+        raise ValueError("Dimensions of obsloc and obsData are not compatible!")   # :1199-1201
+    pick = np.nonzero(~np.isnan(z.ravel()))[0]                                  # :1249
+    M = fmat(obj["M"], "M")
+    K = M.shape[0]
+    s = float(obj["s"])
+    zp = np.asfortranarray(z[pick])
+    Gg = np.empty((K, K), order="F")
+    c = np.empty((K, 1), order="F")
+    if obsloc is None:
+        De = np.ones(Gmat.shape[0]) if "pinfo" not in obj or "D" not in obj["pinfo"] else np.asarray(obj["pinfo"]["D"])
+        w = 1.0 / (s * De[pick])                                                # object$s * De   :1251,1266
+        Gg, c, _ = gram_stats(np.asfortranarray(Gmat[pick]), zp, weights=w)     # G <- object$G[pick, ]  :1252
+    else:
+        if not isinstance(G, MrtsBasis):
+            raise ValueError("Basis matrix of new locations should be given (unless the model was fitted with mrts bases)!")
+        xo = np.asfortranarray(fmat(obsloc, "obsloc")[pick])                    # De <- identity  :1255-1256
+        w = np.full(pick.size, 1.0 / s)
+        zz = C.c_double(0.0)
+        check(lib.frk_plan_predict_gram(G.plan()._h, ptr(xo), xo.shape[0], ptr(zp), 1, ptr(w), ptr(Gg), ptr(c), C.byref(zz)))
+    coef = np.empty((K, 1), order="F")
+    V = np.empty((K, K), order="F") if se_report else None
+    check(lib.frk_krige_from_stats(ptr(Gg), ptr(c), 1, ptr(M), K, int(bool(se_report)), ptr(coef),
+                                   None if V is None else ptr(V)))
+    new = dict(obj)
+    new["w"] = coef
+    if se_report:
+        new["V"] = V
+    return new
+
+
 def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, method="fast", n_neighbor=3,
                 maxknot=5000, DfromLK=None, Fk=None):
     """R/autoFRK.R:199-331 (identity D, complete data, method = "fast").
@@ -318,11 +357,11 @@ def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=N
     se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (:1220), both fused behind the basis evaluation."""
     if "w" not in obj:
         raise ValueError('input model (object) should use the option "wsave=TRUE"!')   # :1171-1173
-    if obsData is not None:
-        raise NotImplementedError("predict.FRK(obsData=...) re-solves with invCz; next row of SURVEY.md 8(f)")
     if newloc is None:
         newloc = obsloc
     G = obj["G"]
+    if obsData is not None:
+        obj = _krige_new_observations(obj, obsData, obsloc, mu_obs, se_report)   # :1248-1274 -> same products below
     if basis is None and newloc is not None and not isinstance(G, MrtsBasis):
         raise ValueError("Basis matrix of new locations should be given (unless the model was fitted with mrts bases)!")
     w = fmat(obj["w"], "w")

@@ -157,6 +157,19 @@ int32_t frk_invCz(const double* Rdiag, const double* L, const double* z, int64_t
 int32_t frk_getLikelihood(const double* Data0, const uint8_t* observed, const double* Fk, const double* M, double s,
                           const double* Ddiag, int64_t n, int32_t K, int32_t T, double* n2loglik);
 
+/* predict.FRK with new observations (R/autoFRK.R:1248-1274) as K x K algebra on the statistics of the basis at
+ * the observation sites: Gg = t(G) iR G (K x K), c = t(G) iR obsData (K x Tc), R = s * De diagonal.  Returns
+ *   coef = t(GM) %*% invCz(R, L, obsData)      (K x Tc;  yhat = basis %*% coef, :1265)
+ *   V    = M - t(GM) %*% invCz(R, L, GM)       (K x K, if want_V; :1270)
+ * with L = G %*% dec$vector %*% diag(sqrt(pmax(dec$value, 0))), dec = eigen(M) (:1260-1264). */
+int32_t frk_krige_from_stats(const double* Gg, const double* c, int32_t Tc, const double* M, int32_t K, int32_t want_V,
+                             double* coef, double* V);
+
+/* host-buffer version of frk_plan_predict_gram_dev: statistics of predict.mrts(object, xnew) against Z with
+ * optional row weights, without ever materialising the n2 x K basis. */
+int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, const double* Z, int32_t T,
+                              const double* weights, double* G, double* C, double* zz);
+
 /* the same two products for a basis matrix the caller already holds (predict.FRK with `basis=` or with
  * newloc = NULL, where R uses object$G): F is n x K, host, column-major; streamed through the device. */
 int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,

@@ -268,3 +268,34 @@ def test_invCz_ZinvC_getLikelihood():
     ref = O.getLikelihood(Zna, F, fit["M"], fit["v"], Dd)
     got = G.getLikelihood(Zna, F, fit["M"], fit["v"], Dd)
     assert abs(got - ref) <= 1e-9 * abs(ref), (got, ref)
+
+
+def test_predict_FRK_with_new_observations():
+    """predict.FRK(obsData=, obsloc=) (R/autoFRK.R:1248-1274): kriging with fresh observations at new sites."""
+    import oracle as O
+    from autofrk_b200 import frk as G, mrts as GM
+
+    rng = np.random.default_rng(2)
+    n, K = 2500, 30
+    loc = rng.random((n, 2))
+    Fo = O.mrts(loc[:300], K, loc)
+    Fg = GM.MrtsBasis(Fo.X, Fo.UZ, Fo.Xu, Fo.nconst, Fo.BBBH)
+    z = (Fo.X[:, 3:6] @ np.array([4.0, -3.0, 2.0]) + rng.standard_normal(n)).reshape(-1, 1)
+    ref, got = O.autoFRK(z, loc, G=Fo), G.autoFRK(z, loc, G=Fg)
+    obsloc = rng.random((900, 2))
+    Bo = O.predict_mrts(Fo, obsloc)
+    obs = Bo[:, 3:6] @ np.array([4.0, -3.0, 2.0]) + rng.standard_normal(900)
+    obs[::17] = np.nan                                           # missing new observations are dropped (:1249)
+    newloc = rng.random((1200, 2))
+    pr = O.predict_FRK(ref, obsData=obs, obsloc=obsloc, newloc=newloc, se_report=True)
+    pg = G.predict_FRK(got, obsData=obs, obsloc=obsloc, newloc=newloc, se_report=True)
+    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-8
+    assert relmax(pg["se"], pr["se"]) < 1e-6
+    # obsloc = NULL: new data at the training sites
+    obs2 = z.ravel() + 0.1 * rng.standard_normal(n)
+    pr2 = O.predict_FRK(ref, obsData=obs2, se_report=True)
+    pg2 = G.predict_FRK(got, obsData=obs2, se_report=True)
+    assert relmax(pg2["pred.value"], pr2["pred.value"]) < 1e-8
+    assert relmax(pg2["se"], pr2["se"]) < 1e-6
+    with pytest.raises(ValueError, match="Dimensions of obsloc and obsData"):
+        G.predict_FRK(got, obsData=obs[:10], obsloc=obsloc)
