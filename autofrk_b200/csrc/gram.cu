@@ -17,6 +17,8 @@
 //   * CTAs of the same row split are adjacent in launch order, so a row block of F is pulled from
 //     HBM once and served to the other tile pairs from the 126 MB L2.
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <vector>
 #include "frk_common.cuh"
 #include "gram.cuh"
@@ -268,60 +270,70 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     FRK_CUDA(cudaGetDevice(&dev));
     FRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-    GramArgs a;
-    a.F = dF; a.ldf = ldf; a.K = K;
-    a.Z = dZ; a.ldz = ldz; a.T = T;
-    a.n = n;
-    a.w = dw;
-    a.ntf = (K + TB - 1) / TB;
-    a.ntz = (T + TB - 1) / TB;
-    a.npairs = a.ntf * (a.ntf + 1) / 2 + a.ntf * a.ntz;
-    // row splits: fill whole waves of one CTA per SM, at least 256 rows per split
-    const int max_split = int(std::max<int64_t>(1, n / 256));
-    int best_ns = 1;
-    double best_eff = 0.0;
-    for (int w = 1; w <= 4; ++w) {
-        int ns = std::max(1, std::min(max_split, (sms * w) / a.npairs));
-        const int ctas = ns * a.npairs;
-        const double eff = double(ctas) / (double((ctas + sms - 1) / sms) * sms);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_ns = ns; }
-    }
-    a.nsplit = best_ns;
-    a.rows_per_split = ((n + a.nsplit - 1) / a.nsplit + KR - 1) / KR * KR;
-    const size_t need = size_t(a.nsplit) * a.npairs * TB * TB;
-    if (ws.partial.n < need) ws.partial.alloc(need);
     const int nzz = 512;
     if (ws.zzpart.n < size_t(nzz)) ws.zzpart.alloc(nzz);
-    a.partial = ws.partial.p;
-
-    const bool aligned = (reinterpret_cast<uintptr_t>(dF) % 16 == 0) && (ldf % 2 == 0) &&
-                         (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));
-    static bool attr_set = false;
-    if (!attr_set) {
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-        FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-        attr_set = true;
-    }
     if (T > 0) {
         sumsq_kernel<<<nzz, 256, 0, st>>>(dZ, ldz, n, T, dw, ws.zzpart.p);
     } else {
         FRK_CUDA(cudaMemsetAsync(ws.zzpart.p, 0, sizeof(double) * nzz, st));
     }
     FRK_CUDA(cudaGetLastError());
-    const int grid = a.nsplit * a.npairs;
-    if (aligned && !dw) gram_kernel<true, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
-    else if (!aligned && !dw) gram_kernel<false, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
-    else if (aligned) gram_kernel<true, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
-    else gram_kernel<false, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
-    FRK_CUDA(cudaGetLastError());
-    gram_reduce_kernel<<<a.npairs, 256, 0, st>>>(ws.partial.p, a.nsplit, a.npairs, a.ntf, a.ntz, K, T, ws.zzpart.p, nzz,
-                                                 dpacked);
+
+    static const bool force_cpasync = [] {
+        const char* e = std::getenv("FRK_GRAM_PATH");
+        return e && std::string(e) == "cpasync";
+    }();
+    GramLayout lay;
+    if (!force_cpasync && gram_tma_usable(dF, ldf, dZ, T, ldz, n)) {
+        gram_stats_tma_dev(dF, n, K, ldf, dZ, T, ldz, dw, ws, sms, lay, st);
+    } else {
+        GramArgs a;
+        a.F = dF; a.ldf = ldf; a.K = K;
+        a.Z = dZ; a.ldz = ldz; a.T = T;
+        a.n = n;
+        a.w = dw;
+        a.ntf = (K + TB - 1) / TB;
+        a.ntz = (T + TB - 1) / TB;
+        a.npairs = a.ntf * (a.ntf + 1) / 2 + a.ntf * a.ntz;
+        // row splits: fill whole waves of one CTA per SM, at least 256 rows per split
+        const int max_split = int(std::max<int64_t>(1, n / 256));
+        int best_ns = 1;
+        double best_eff = 0.0;
+        for (int w = 1; w <= 4; ++w) {
+            int ns = std::max(1, std::min(max_split, (sms * w) / a.npairs));
+            const int ctas = ns * a.npairs;
+            const double eff = double(ctas) / (double((ctas + sms - 1) / sms) * sms);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_ns = ns; }
+        }
+        a.nsplit = best_ns;
+        a.rows_per_split = ((n + a.nsplit - 1) / a.nsplit + KR - 1) / KR * KR;
+        const size_t need = size_t(a.nsplit) * a.npairs * TB * TB;
+        if (ws.partial.n < need) ws.partial.alloc(need);
+        a.partial = ws.partial.p;
+        const bool aligned = (reinterpret_cast<uintptr_t>(dF) % 16 == 0) && (ldf % 2 == 0) &&
+                             (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));
+        static bool attr_set = false;
+        if (!attr_set) {
+            FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+            FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+            FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+            FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
+            attr_set = true;
+        }
+        const int grid = a.nsplit * a.npairs;
+        if (aligned && !dw) gram_kernel<true, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+        else if (!aligned && !dw) gram_kernel<false, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+        else if (aligned) gram_kernel<true, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+        else gram_kernel<false, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
+        FRK_CUDA(cudaGetLastError());
+        lay.ntf = a.ntf; lay.ntz = a.ntz; lay.npairs = a.npairs; lay.nsplit = a.nsplit;
+    }
+    gram_reduce_kernel<<<lay.npairs, 256, 0, st>>>(ws.partial.p, lay.nsplit, lay.npairs, lay.ntf, lay.ntz, K, T, ws.zzpart.p,
+                                                   nzz, dpacked);
     FRK_CUDA(cudaGetLastError());
     ws.launches += 3;
-    ws.last_nsplit = a.nsplit;
-    ws.last_npairs = a.npairs;
+    ws.last_nsplit = lay.nsplit;
+    ws.last_npairs = lay.npairs;
 }
 
 }  // namespace frk

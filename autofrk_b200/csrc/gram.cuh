@@ -4,9 +4,15 @@
 
 namespace frk {
 
+struct GramLayout {
+    int ntf = 0, ntz = 0, npairs = 0, nsplit = 0;
+};
+
 struct GramWorkspace {
     DevBuf<double> partial;  // row-split partial tiles
     DevBuf<double> zzpart;   // per-block partial sums of squares
+    DevBuf<int> pair_order;  // TMA path: tile-pair order + work counter
+    int order_ntf = -1, order_ntz = -1;  // shape the cached order was built for
     int64_t launches = 0;
     int last_nsplit = 0, last_npairs = 0;
 };
@@ -18,5 +24,10 @@ size_t gram_packed_len(int K, int T);
 // dw: optional row weights (n doubles, device) or nullptr.
 void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
                     const double* dw, double* dpacked, GramWorkspace& ws, cudaStream_t st);
+
+// TMA variant (gram_tma.cu): needs 16-byte aligned bases and even leading dimensions
+bool gram_tma_usable(const double* dF, int64_t ldf, const double* dZ, int T, int64_t ldz, int64_t n);
+void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
+                        const double* dw, GramWorkspace& ws, int sms, GramLayout& lay, cudaStream_t st);
 
 }  // namespace frk
