@@ -1,0 +1,86 @@
+"""Maximum-size and 64-bit-indexing checks on the GPU through size-independent properties (no oracle needed)."""
+import numpy as np
+import pytest
+
+from util import TOL, colrel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_max_knots_fit_and_identity():
+    """maxknot = 5000 knots (R/autoFRK.R:1050 default), k* = 1200 (three column slices): the fit's invariants and
+    the known-answer identity predict(mrts(knot, k), knot) == mrts(knot, k)."""
+    from autofrk_b200 import mrts as G
+
+    rng = np.random.default_rng(0)
+    m, d, kstar = 5000, 2, 1200
+    Xu = rng.random((m, d))
+    fit = G.mrtsrcpp(Xu, G.xobs_diag_of(Xu, m), kstar)
+    g = fit["X"][:, d + 1:] / np.sqrt(m)
+    assert np.max(np.abs(g.T @ g - np.eye(kstar))) < TOL
+    B = np.column_stack([np.ones(m), Xu])
+    assert np.max(np.abs(B.T @ g)) < 1e-8
+    obj = G.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
+    assert obj.plan().info["slices"] == 3
+    at = G.predict_mrts(obj, Xu)
+    assert colrel(at, fit["X"]) < 1e-9          # 5000-term sums against eigenvalues down to ~1e-6 of the largest
+
+
+def test_int64_indexing_and_row_equivariance():
+    """5M x 497 output (2.5e9 elements > 2^31): rows far beyond the 32-bit element range equal the same rows
+    evaluated on their own, and a row permutation of the input permutes the output (bitwise)."""
+    import torch
+    from autofrk_b200 import mrts as G
+
+    rng = np.random.default_rng(1)
+    d, m, kstar = 2, 1000, 497
+    Xu = rng.random((m, d))
+    UZ = np.zeros((m + d + 1, kstar + d + 1))
+    UZ[:m, :kstar] = rng.standard_normal((m, kstar))
+    plan = G.MrtsPlan(Xu, rng.standard_normal((d + 1, m)), UZ, np.ones(d), kstar)
+    n2 = 5_000_000
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=g).T
+    out = plan.predict_dev(x)
+    torch.cuda.synchronize()
+    tail = slice(n2 - 1000, n2)
+    assert int(tail.start) * kstar > 2 ** 31
+    sub = plan.predict_dev(x[tail].T.contiguous().T)
+    assert torch.equal(out[tail], sub)
+    perm = torch.randperm(200_000, device="cuda", generator=g)
+    xs = x[:200_000]
+    a = plan.predict_dev(xs[perm].T.contiguous().T)
+    assert torch.equal(a, out[:200_000][perm])
+    del out, sub, a
+    torch.cuda.empty_cache()
+
+
+def test_gram_additivity_and_trace_at_scale():
+    """2M x 500 basis: Gram of the whole equals the sum over three ragged row shards; trace(G) = ||F||_F^2."""
+    import ctypes as C
+    import torch
+    from autofrk_b200 import _lib
+
+    n, K, T = 2_000_001, 500, 7
+    g = torch.Generator(device="cuda").manual_seed(4)
+    F = torch.randn((K, n + 1), dtype=torch.float64, device="cuda", generator=g).T      # ld = n + 1 (even)
+    Z = torch.randn((T, n + 1), dtype=torch.float64, device="cuda", generator=g).T
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def stats(r0, r1):
+        p = torch.empty(plen, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F[r0:].data_ptr()), r1 - r0, K, n + 1, C.c_void_p(Z[r0:].data_ptr()),
+                                               T, n + 1, None, C.c_void_p(p.data_ptr()), st))
+        return p
+
+    whole = stats(0, n)
+    parts = stats(0, 700_000) + stats(700_000, 1_300_002) + stats(1_300_002, n)
+    torch.cuda.synchronize()
+    scale = whole[:K * K].abs().max()
+    assert float((whole - parts).abs().max() / scale) < 1e-12
+    Gm = whole[:K * K].reshape(K, K)
+    assert torch.equal(Gm, Gm.T)
+    fro = float((F[:n] ** 2).sum())
+    assert abs(float(torch.trace(Gm)) - fro) / fro < 1e-12
+    assert abs(float(whole[-1]) - float((Z[:n] ** 2).sum())) / float(whole[-1]) < 1e-12
