@@ -68,6 +68,9 @@ _SIGNATURES = {
     "frk_getLikelihood": (_i32, [_vp, _vp, _vp, _vp, C.c_double, _vp, _i64, _i32, _i32, _vp]),
     "frk_krige_from_stats": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "frk_plan_predict_gram": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "frk_masked_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "frk_EM0miss_stats": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, C.c_double, _i32, C.c_double, _i32, C.c_double,
+                                 _vp, _vp, _vp, _vp]),
     "frk_basis_predict_frk": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -200,6 +200,58 @@ def getLikelihood(Data, Fk, M, s, Depsilon):
     return out.value
 
 
+def mkpd(M):
+    """R/helper.R:278-288 (the eigenvalues come from the device eigensolver)."""
+    M = fmat(M, "M")
+    v = float(getASCeigens((M + M.T) / 2 if not np.array_equal(M, M.T) else M)["value"][0])
+    if v <= 0:
+        M = M + np.eye(M.shape[0]) * (max(0.0, -v) + 0.1 ** 7.5)
+    return M
+
+
+def EM0miss(Fk, Data, Depsilon, maxit=50, avgtol=1e-6, wSave=False, external=False, DfromLK=None, num_report=True,
+            vfixed=None):
+    """R/autoFRK.R:560-737 for diagonal Depsilon and DfromLK = NULL.
+
+    The per-replicate masked products of :587-616 come from one row-weighted pass over Fk; the EM iteration
+    (:652-687) is K x K work on the device; the final likelihood is getLikelihood (:690)."""
+    if DfromLK is not None:
+        raise NotImplementedError("LatticeKrig fine scale is out of scope (SURVEY.md 2 #20)")
+    if external:
+        raise NotImplementedError("external=TRUE calls the undefined dumpObjects upstream (R/autoFRK.R:619): dead code")
+    F = fmat(Fk.X if isinstance(Fk, MrtsBasis) else Fk, "Fk")
+    Z = fmat(Data, "Data")
+    n, K = F.shape
+    TT = Z.shape[1]
+    Dd = _diag_of(Depsilon, n, "Depsilon")
+    O = np.asfortranarray(~np.isnan(Z), dtype=np.uint8)          # :564
+    Z0 = np.asfortranarray(np.where(np.isnan(Z), 0.0, Z))        # :643-644
+    G_all = np.empty((K, K, TT), order="F")
+    c_all = np.empty((K, TT), order="F")
+    zz_all = np.empty(TT)
+    nobs = np.empty(TT, dtype=np.int64)
+    check(lib.frk_masked_stats(ptr(Z0), O.ctypes.data_as(C.c_void_p), ptr(F), ptr(Dd), n, K, TT, ptr(G_all), ptr(c_all),
+                               ptr(zz_all), nobs.ctypes.data_as(C.c_void_p)))
+    old = cMLEimat(F, Z0, s=0.0, wSave=True)                     # :645
+    s0 = old["v"] if vfixed is None else float(vfixed)           # :646
+    M = np.empty((K, K), order="F")
+    etatt = np.empty((K, TT), order="F")
+    s_out, niter = C.c_double(0.0), C.c_int32(0)
+    check(lib.frk_EM0miss_stats(ptr(G_all), ptr(c_all), ptr(zz_all), int(nobs.sum()), K, TT, ptr(fmat(old["M"])), float(s0),
+                                int(maxit), float(avgtol), int(vfixed is not None), 0.0 if vfixed is None else float(vfixed),
+                                ptr(M), C.byref(s_out), ptr(etatt), C.byref(niter)))
+    if num_report:
+        print("Number of iteration: ", niter.value)              # :688
+    n2loglik = getLikelihood(Z, F, M, s_out.value, Dd)           # :690
+    out = {"M": M, "s": s_out.value, "negloglik": n2loglik}
+    if wSave:                                                    # :726-735
+        out["w"] = etatt
+        out["V"] = M - etatt @ etatt.T / TT
+        out["missing"] = {"miss": 1 - O, "maxit": maxit, "avgtol": avgtol}
+    out["niter"] = niter.value
+    return out
+
+
 def kgrid(d, maxK):
     """Default K sequence, R/autoFRK.R:254-257."""
     K = np.unique(np.round(np.arange(d + 1, maxK + 1e-9, maxK ** (1.0 / 3) * d))).astype(int)
@@ -311,9 +363,18 @@ def indeMLE(Data, Fk, D=None, maxit=50, avgtol=1e-6, wSave=False, DfromLK=None, 
     if DfromLK is not None:
         raise NotImplementedError("LatticeKrig fine scale (cMLElk) is out of scope (SURVEY.md 2 #20)")
     Z = fmat(Data, "Data")
-    if np.isnan(Z).any():
-        raise NotImplementedError("missing values (EM0miss) are out of scope (SURVEY.md 2 #21)")
     F = Fk.X if isinstance(Fk, MrtsBasis) else fmat(Fk, "Fk")
+    if np.isnan(Z).any():                                       # withNA -> EM0miss (:829-841)
+        keep_t = ~np.all(np.isnan(Z), axis=0)                   # empty replicates are dropped (:746-750) ...
+        keep_r = ~np.all(np.isnan(Z[:, keep_t]), axis=1)        # ... and so are rows never observed (:754-770)
+        Dd = np.ones(Z.shape[0]) if D is None else _diag_of(D, Z.shape[0], "D")
+        out = EM0miss(F[keep_r], Z[np.ix_(keep_r, keep_t)], Dd[keep_r], maxit, avgtol, wSave, False, None, False, vfixed)
+        if wSave:
+            w = np.zeros((F.shape[1], Z.shape[1]))
+            w[:, keep_t] = out["w"]                             # :834-836
+            out["w"] = w
+            out["pinfo"] = {"D": Dd, "pick": np.nonzero(keep_r)[0]}   # :838
+        return out
     if D is not None:
         Dd = np.asarray(D, dtype=np.float64)
         if Dd.ndim == 2:

@@ -170,6 +170,18 @@ int32_t frk_krige_from_stats(const double* Gg, const double* c, int32_t Tc, cons
 int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, const double* Z, int32_t T,
                               const double* weights, double* G, double* C, double* zz);
 
+/* EM0miss (R/autoFRK.R:560-737; diagonal Depsilon, DfromLK = NULL) in two steps.
+ * (1) per-replicate NA-masked statistics (:587-616) in one pass over the rows of Fk:
+ *     G_all[, , t] = t(Bt) iDt Bt (K x K), c_all[, t] = t(iDBt) zt (K), zz_all[t] = t(zt) iDt zt, nobs_all[t] = sum(O[, t]);
+ *     Data0 = Data with NA -> 0, observed = !is.na(Data) as bytes, Ddiag = diag(Depsilon). */
+int32_t frk_masked_stats(const double* Data0, const uint8_t* observed, const double* Fk, const double* Ddiag, int64_t n,
+                         int32_t K, int32_t T, double* G_all, double* c_all, double* zz_all, int64_t* nobs_all);
+/* (2) the EM iteration (:652-687) from those statistics, started at M0 = cMLEimat(Fk, Z0, 0, TRUE)$M and s0
+ *     (its v, or vfixed): returns M (K x K), s, etatt (K x T) and the iteration count. */
+int32_t frk_EM0miss_stats(const double* G_all, const double* c_all, const double* zz_all, int64_t sumO, int32_t K, int32_t T,
+                          const double* M0, double s0, int32_t maxit, double avgtol, int32_t has_vfixed, double vfixed,
+                          double* M_out, double* s_out, double* etatt_out, int32_t* niter);
+
 /* the same two products for a basis matrix the caller already holds (predict.FRK with `basis=` or with
  * newloc = NULL, where R uses object$G): F is n x K, host, column-major; streamed through the device. */
 int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,

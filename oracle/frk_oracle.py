@@ -287,6 +287,80 @@ def getLikelihood(Data, Fk, M, s, Depsilon_diag):
     return n2loglik
 
 
+def mkpd(M):
+    """R/helper.R:278-288."""
+    M = np.asarray(M, dtype=np.float64)
+    v = np.min(sla.eigvalsh((M + M.T) / 2 if not np.allclose(M, M.T, rtol=0, atol=0) else M))
+    if v <= 0:
+        M = M + np.eye(M.shape[0]) * (max(0.0, -v) + 0.1 ** 7.5)
+    return M
+
+
+def ginv(X, tol=math.sqrt(np.finfo(float).eps)):
+    """MASS::ginv: SVD pseudo-inverse, singular values <= tol * max dropped."""
+    U, d, Vt = np.linalg.svd(np.asarray(X, dtype=np.float64))
+    pos = d > max(tol * d[0], 0.0)
+    return (Vt[pos].T * (1.0 / d[pos])) @ U[:, pos].T
+
+
+def EM0miss(Fk, Data, Ddiag, maxit=50, avgtol=1e-6, wSave=False, vfixed=None):
+    """R/autoFRK.R:560-737, DfromLK = NULL, external = FALSE, diagonal Depsilon (its diagonal `Ddiag`)."""
+    Fk = np.asarray(Fk, dtype=np.float64)
+    Data = _as2d(Data)
+    O = ~np.isnan(Data)                                        # :564
+    TT, K = Data.shape[1], Fk.shape[1]
+    iD = 1.0 / np.asarray(Ddiag, dtype=np.float64).ravel()     # :575
+    ziDz = np.zeros(TT)
+    ziDB = np.zeros((TT, K))
+    db = []
+    for tt in range(TT):                                       # :587-636
+        o = O[:, tt]
+        iDt = iD[o]                                            # :607
+        Bt = Fk[o, :]                                          # :609
+        iDBt = iDt[:, None] * Bt                               # :611
+        zt = Data[o, tt]                                       # :612
+        ziDz[tt] = np.sum(zt * (iDt * zt))                     # :613
+        ziDB[tt] = zt @ iDBt                                   # :614
+        db.append((iDBt, zt, Bt.T @ iDBt))                     # :615, :628-634
+    Z0 = np.where(np.isnan(Data), 0.0, Data)                   # :643-644
+    old = cMLEimat(Fk, Z0, s=0.0, wSave=True)                  # :645
+    old["s"] = old["v"] if vfixed is None else vfixed          # :646
+    old["M"] = mkpd(old["M"])                                  # :647
+    Ptt1 = old["M"]
+    dif, cnt = math.inf, 0
+    new, etatt = old, np.zeros((K, TT))
+    while dif > avgtol * (100 * K ** 2) and cnt < maxit:       # :652
+        etatt = np.zeros((K, TT))
+        sumPtt = np.zeros((K, K))
+        s1 = np.zeros(TT)
+        for tt in range(TT):                                   # :657-669
+            iDBt, zt, BiDBt = db[tt]
+            iP = mkpd(ginv(mkpd(Ptt1)) + BiDBt / old["s"])     # :659
+            Ptt = np.linalg.inv(iP)                            # :660
+            Gt = Ptt @ iDBt.T / old["s"]                       # :661
+            eta = Gt @ zt                                      # :662
+            s1kk = np.diag(BiDBt @ (np.outer(eta, eta) + Ptt))  # :663
+            sumPtt += Ptt                                      # :666
+            etatt[:, tt] = eta                                 # :667
+            s1[tt] = np.sum(s1kk)                              # :668
+        M = (etatt @ etatt.T + sumPtt) / TT                    # :672
+        if vfixed is None:
+            sn = max((np.sum(ziDz) - 2 * np.sum(ziDB * etatt.T) + np.sum(s1)) / np.sum(O), 0.1 ** 8)  # :673
+        else:
+            sn = vfixed                                        # :678
+        M = (M + M.T) / 2                                      # :681
+        dif = np.sum(np.abs(M - old["M"])) + abs(sn - old["s"])  # :682
+        cnt += 1
+        old = new = {"M": M, "s": sn}
+        Ptt1 = M                                               # :685
+    n2loglik = getLikelihood(Data, Fk, new["M"], new["s"], Ddiag)   # :690
+    out = {"M": new["M"], "s": new["s"], "negloglik": n2loglik, "niter": cnt}
+    if wSave:
+        out["w"] = etatt                                       # :729
+        out["V"] = new["M"] - etatt @ etatt.T / TT
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # model-fit orchestration (identity D, no missing values)
 # --------------------------------------------------------------------------------------------

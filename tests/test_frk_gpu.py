@@ -299,3 +299,34 @@ def test_predict_FRK_with_new_observations():
     assert relmax(pg2["se"], pr2["se"]) < 1e-5              # V = M - (...) cancels on both sides
     with pytest.raises(ValueError, match="Dimensions of obsloc and obsData"):
         G.predict_FRK(got, obsData=obs[:10], obsloc=obsloc)
+
+
+def test_EM0miss_matches_oracle():
+    """the missing-data EM (R/autoFRK.R:560-737) from per-replicate masked statistics."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(6)
+    n, K, T = 2500, 11, 7
+    F, Z = _data(n, K, T, seed=31, rank=3)
+    Z[rng.random(Z.shape) < 0.3] = np.nan
+    D = rng.random(n) + 0.5
+    for Dd, vfix in ((np.ones(n), None), (D, None), (np.ones(n), 1.3)):
+        ref = O.EM0miss(F, Z, Dd, maxit=50, avgtol=1e-6, wSave=True, vfixed=vfix)
+        got = G.EM0miss(F, Z, Dd, maxit=50, avgtol=1e-6, wSave=True, num_report=False, vfixed=vfix)
+        assert got["niter"] == ref["niter"]
+        assert abs(got["s"] - ref["s"]) <= 1e-9 * abs(ref["s"])
+        assert relmax(got["M"], ref["M"]) < 1e-8
+        assert relmax(got["w"], ref["w"]) < 1e-8
+        assert relmax(got["V"], ref["V"]) < 1e-7
+        assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-9 * abs(ref["negloglik"])
+    # indeMLE dispatches data with NAs to EM0miss (R/autoFRK.R:829-841); an all-NA replicate keeps a zero column in w
+    Z2 = Z.copy()
+    Z2[:, 2] = np.nan
+    r = G.indeMLE(Z2, F, wSave=True)
+    assert r["w"].shape == (K, T) and np.all(r["w"][:, 2] == 0.0)
+    Zk = Z2[:, [0, 1, 3, 4, 5, 6]]
+    rows = ~np.all(np.isnan(Zk), axis=1)                   # indeMLE drops never-observed rows first (R/autoFRK.R:754-770)
+    ref2 = O.EM0miss(F[rows], Zk[rows], np.ones(int(rows.sum())), wSave=True)
+    assert relmax(r["M"], ref2["M"]) < 1e-8
+    assert np.array_equal(r["pinfo"]["pick"], np.nonzero(rows)[0])
