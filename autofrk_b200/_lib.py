@@ -71,6 +71,7 @@ _SIGNATURES = {
     "frk_masked_stats": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "frk_EM0miss_stats": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, C.c_double, _i32, C.c_double, _i32, C.c_double,
                                  _vp, _vp, _vp, _vp]),
+    "frk_knn_impute": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32]),
     "frk_basis_predict_frk": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -252,6 +252,18 @@ def EM0miss(Fk, Data, Depsilon, maxit=50, avgtol=1e-6, wSave=False, external=Fal
     return out
 
 
+def knn_impute(Data, loc, n_neighbor=3):
+    """R/autoFRK.R:135-148 (= :273-286): NA -> mean of the n.neighbor nearest observed values of the same replicate."""
+    Z = np.array(fmat(Data, "Data"), order="F", copy=True)
+    if not np.isnan(Z).any():
+        return Z
+    L = fmat(loc, "loc")
+    if L.shape[0] != Z.shape[0]:
+        raise _lib.FrkError(_lib.FRK_EINVAL, "loc must have one row per row of Data")
+    check(lib.frk_knn_impute(ptr(L), L.shape[0], L.shape[1], ptr(Z), Z.shape[1], int(n_neighbor)))
+    return Z
+
+
 def kgrid(d, maxK):
     """Default K sequence, R/autoFRK.R:254-257."""
     K = np.unique(np.round(np.arange(d + 1, maxK + 1e-9, maxK ** (1.0 / 3) * d))).astype(int)
@@ -315,17 +327,20 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
                 raise NotImplementedError("non-diagonal D needs spam's sparse solve, out of scope (SURVEY.md 2 #19)")
             Dd = np.diag(Dd)
         iD = 1.0 / Dd
-    if method != "fast":
-        raise NotImplementedError('method="EM" (EM0miss) is out of scope (SURVEY.md 2 #21)')
+    if method not in ("fast", "EM"):
+        raise ValueError("'arg' should be one of 'fast', 'EM'")   # match.arg(method)
     Z = fmat(Data, "Data")
-    if np.isnan(Z).any():
-        raise NotImplementedError("missing values need kNN imputation / EM0miss, out of scope (SURVEY.md 2 #21, #25)")
     loc = fmat(loc, "loc")
+    keep_t = ~np.all(np.isnan(Z), axis=0)                       # empty replicates dropped (:203-206)
+    Z = Z[:, keep_t]
+    pick = np.nonzero(~np.all(np.isnan(Z), axis=1))[0]          # rows never observed dropped (:213-220)
+    Z = np.asfortranarray(Z[pick])
+    withNA = bool(np.isnan(Z).any())
     d = loc.shape[1]
     N = Z.shape[0]
     klim = int(min(N, np.round(10 * math.sqrt(N))))             # :222
     if N < maxknot:
-        knot = loc                                              # :223-224
+        knot = loc[pick]                                        # :223-224
     else:
         raise NotImplementedError("N >= maxknot needs subKnot (R RNG), out of scope: pass G = mrts(knot, K, loc)")
     if maxK is not None:
@@ -345,8 +360,23 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
         K = kgrid(d, maxK)                                      # :254-257
     if Fk is None:
         Fk = mrts(knot, int(K.max()), loc, maxknot)             # :260
+    if method == "EM":                                          # :264-271: one indeMLE (EM0miss when there are NAs) per K
+        Dp = None if D is None else (1.0 / iD)[pick]
+        AIC = np.full(K.size, np.inf)
+        for i, k in enumerate(K):
+            AIC[i] = indeMLE(Z, np.asfortranarray(Fk.X[pick][:, :int(k)]), Dp, maxit, avgtol, wSave=False)["negloglik"]
+        TT = Z.shape[1]
+        df = np.where(K <= TT, K * (K + 1) / 2 + 1, K * TT + 1 - TT * (TT - 1) / 2)   # :321
+        AIC = AIC + 2 * df
+        out = Fk.leading(int(K[np.argmin(AIC)]))
+        out.AIC, out.Kgrid = AIC, K
+        return out
+    if withNA:
+        Z = knn_impute(Z, loc[pick], n_neighbor)                # :273-286
     TT = Z.shape[1]
-    G, Cm, zz = gram_stats(Fk.X, Z, weights=iD)                 # one pass; trS = zz/TT (:304)
+    if iD is not None:
+        iD = iD[pick]
+    G, Cm, zz = gram_stats(np.asfortranarray(Fk.X[pick]), Z, weights=iD)   # one pass; trS = zz/TT (:304)
     AIC = np.full(K.size, np.inf)
     for i, k in enumerate(K):                                   # :305-317
         AIC[i] = cmle_from_stats(G, Cm, zz, N, TT, s=0.0, wSave=False, onlylogLike=True, K=int(k))["negloglik"]
@@ -407,6 +437,8 @@ def autoFRK(Data, loc, mu=0.0, D=None, G=None, finescale=False, maxit=50, tolera
         Fk = G                                                  # :126-127
     else:
         Fk = selectBasis(Z, loc, D, maxit, tolerance, maxK, Kseq, method, n_neighbor, maxknot, None)  # :129-132
+    if method == "fast":
+        Z = knn_impute(Z, loc, n_neighbor)                      # :135-148
     obj = indeMLE(Z, Fk, D, maxit, avgtol=tolerance, wSave=True)  # :151
     obj["G"] = Fk                                               # :185
     obj["LKobj"] = None

@@ -182,6 +182,11 @@ int32_t frk_EM0miss_stats(const double* G_all, const double* c_all, const double
                           const double* M0, double s0, int32_t maxit, double avgtol, int32_t has_vfixed, double vfixed,
                           double* M_out, double* s_out, double* etatt_out, int32_t* niter);
 
+/* kNN mean imputation, the method = "fast" pre-step of autoFRK() / selectBasis() (R/autoFRK.R:135-148, :273-286):
+ * every NA of Data (n x T, column-major, modified in place) becomes the mean of the n.neighbor = k nearest
+ * observed values of its replicate (FNN::get.knnx on loc, n x d). */
+int32_t frk_knn_impute(const double* loc, int64_t n, int32_t d, double* Data, int32_t T, int32_t k);
+
 /* the same two products for a basis matrix the caller already holds (predict.FRK with `basis=` or with
  * newloc = NULL, where R uses object$G): F is n x K, host, column-major; streamed through the device. */
 int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const double* w, int32_t T, const double* V,

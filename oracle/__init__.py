@@ -23,5 +23,5 @@ from .mrts_oracle import (  # noqa: F401
 )
 from .frk_oracle import (  # noqa: F401
     getASCeigens, getEigen, getHalf, sol_v, sol_eta, neg2llik, cMLE, cMLEimat, invCz, ZinvC,
-    getLikelihood, selectBasis, indeMLE, autoFRK, predict_FRK, gram_stats, cmle_from_stats, cMLEsp, EM0miss, mkpd, ginv,
+    getLikelihood, selectBasis, indeMLE, autoFRK, predict_FRK, gram_stats, cmle_from_stats, cMLEsp, EM0miss, mkpd, ginv, knn_impute,
 )

@@ -377,15 +377,38 @@ def kgrid(d, maxK):
     return K
 
 
-def selectBasis(Data, loc, maxK=None, Kseq=None, maxknot=5000, Fk=None):
-    """R/autoFRK.R:199-331, D = I, no NA, method='fast'."""
+def knn_impute(Data, loc, n_neighbor=3):
+    """R/autoFRK.R:135-148 / :273-286: FNN::get.knnx by brute force (ties -> lower index)."""
+    Data = np.array(_as2d(Data), copy=True)
+    loc = _as2d(loc)
+    for tt in range(Data.shape[1]):
+        where = np.isnan(Data[:, tt])
+        if not where.any():
+            continue
+        cidx = np.nonzero(~where)[0]
+        q, r = loc[where], loc[cidx]
+        d2 = ((q[:, None, :] - r[None, :, :]) ** 2).sum(axis=2)
+        nn = np.argsort(d2, axis=1, kind="stable")[:, :n_neighbor]
+        Data[where, tt] = Data[cidx[nn], tt].mean(axis=1)
+    return Data
+
+
+def selectBasis(Data, loc, maxK=None, Kseq=None, maxknot=5000, Fk=None, n_neighbor=3):
+    """R/autoFRK.R:199-331, D = I, method='fast'.
+
+    Replicates without data and rows never observed are dropped first (:203-220), so the knots are the observed
+    locations; remaining NAs are imputed by kNN means (:273-286).  NB upstream indexes the UNPRUNED `loc` with
+    pruned row numbers at :281 (misaligned when rows were dropped); the restatement uses the aligned locations."""
     Data = _as2d(Data)
     loc = _as2d(loc)
+    Data = Data[:, ~np.all(np.isnan(Data), axis=0)]            # :203-206
+    pick = np.nonzero(~np.all(np.isnan(Data), axis=1))[0]      # :213-220
+    Data = Data[pick]
     d = loc.shape[1]
-    N = Data.shape[0]
+    N = pick.size                                              # :221
     klim = int(min(N, _r_round(10 * math.sqrt(N))))            # :222
     if N < maxknot:
-        knot = loc                                             # :223-224
+        knot = loc[pick]                                       # :223-224
     else:
         raise NotImplementedError("subKnot (R RNG) is out of scope")
     if maxK is not None:
@@ -405,7 +428,9 @@ def selectBasis(Data, loc, maxK=None, Kseq=None, maxknot=5000, Fk=None):
         K = kgrid(d, maxK)                                     # :254-257
     if Fk is None:
         Fk = mrts(knot, int(K.max()), loc, maxknot)            # :260
-    F = Fk.X
+    if np.isnan(Data).any():
+        Data = knn_impute(Data, loc[pick], n_neighbor)         # :273-286
+    F = Fk.X[pick]
     TT = Data.shape[1]
     iDFk = F                                                   # iD = I (:289-291)
     trS = np.sum(np.sum(Data * Data, axis=1)) / TT             # :304
@@ -442,6 +467,8 @@ def autoFRK(Data, loc, mu=0.0, G=None, maxK=None, Kseq=None, maxknot=5000):
     """R/autoFRK.R:121-197, finescale=FALSE, method='fast', D = I, no NA."""
     Data = _as2d(Data) - mu                                    # :125
     Fk = G if G is not None else selectBasis(Data, loc, maxK=maxK, Kseq=Kseq, maxknot=maxknot)  # :126-133
+    if np.isnan(Data).any():
+        Data = knn_impute(Data, loc)                           # :135-148 (method = "fast")
     F = Fk.X if isinstance(Fk, MrtsObject) else np.asarray(Fk)
     obj = indeMLE(Data, F, wSave=True)                         # :151
     obj["G"] = Fk                                              # :185

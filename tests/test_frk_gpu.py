@@ -330,3 +330,40 @@ def test_EM0miss_matches_oracle():
     ref2 = O.EM0miss(F[rows], Zk[rows], np.ones(int(rows.sum())), wSave=True)
     assert relmax(r["M"], ref2["M"]) < 1e-8
     assert np.array_equal(r["pinfo"]["pick"], np.nonzero(rows)[0])
+
+
+def test_knn_imputation_and_autoFRK_with_missing_values():
+    """method = "fast" with NAs: kNN mean imputation (R/autoFRK.R:135-148) then the complete-data fit."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(8)
+    for d in (1, 2, 3):
+        n, T = 3000, 4
+        loc = rng.random((n, d))
+        Z = np.sin(3 * loc[:, :1]) @ np.ones((1, T)) + 0.1 * rng.standard_normal((n, T))
+        Z[rng.random(Z.shape) < 0.15] = np.nan
+        for k in (1, 3, 5):
+            ref, got = O.knn_impute(Z, loc, k), G.knn_impute(Z, loc, k)
+            assert not np.isnan(got).any()
+            assert np.max(np.abs(got - ref)) < 1e-14
+    n = 1500
+    loc = rng.random((n, 2))
+    z = (3.0 * np.sin(4 * loc[:, 0]) * np.cos(3 * loc[:, 1]) + rng.standard_normal(n)).reshape(-1, 1)
+    z[rng.random(n) < 0.1] = np.nan
+    ref = O.autoFRK(z, loc, maxK=40)
+    got = G.autoFRK(z, loc, maxK=40)
+    assert got["G"].X.shape == ref["G"].X.shape
+    assert abs(got["s"] - ref["s"]) <= 1e-8 * abs(ref["s"])
+    pr, pg = O.predict_FRK(ref, newloc=loc[:200]), G.predict_FRK(got, newloc=loc[:200])
+    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-7
+    # method = "EM": AIC sweep and final fit through EM0miss
+    gotem = G.autoFRK(z, loc, Kseq=[5, 9, 14], method="EM")
+    assert gotem["G"].X.shape[1] in (5, 9, 14) and np.isfinite(gotem["negloglik"]) and gotem["w"].shape[1] == 1
+    with pytest.raises(_frk_error(), match="fewer observed values"):
+        G.knn_impute(np.array([[1.0], [np.nan], [np.nan]]), np.arange(3.0).reshape(-1, 1), 3)
+
+
+def _frk_error():
+    from autofrk_b200._lib import FrkError
+    return FrkError
