@@ -115,10 +115,20 @@ SEXP _autoFRK_gram_stats(SEXP Fk, SEXP Data) {
     SEXP G = PROTECT(Rf_allocMatrix(REALSXP, K, K));
     SEXP C = PROTECT(Rf_allocMatrix(REALSXP, K, T));
     SEXP zz = PROTECT(Rf_allocVector(REALSXP, 1));
-    check(frk_gram_stats(REAL(Fk), n, K, REAL(Data), T, REAL(G), REAL(C), REAL(zz)));
+    check(frk_gram_stats(REAL(Fk), n, K, REAL(Data), T, NULL, REAL(G), REAL(C), REAL(zz)));
     SET_VECTOR_ELT(out, 0, G); SET_VECTOR_ELT(out, 1, C); SET_VECTOR_ELT(out, 2, zz);
     UNPROTECT(4);
     return out;
+}
+
+/* getHalf from the K x K cross-product t(Fk) %*% iDFk   (R/helper.R:19-26) */
+SEXP _autoFRK_getHalf_stats(SEXP G) {
+    need_real_matrix(G, "G");
+    int K = Rf_nrows(G);
+    SEXP half = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    check(frk_getHalf(REAL(G), K, K, REAL(half)));
+    UNPROTECT(1);
+    return half;
 }
 
 SEXP _autoFRK_cMLEimat_stats(SEXP G, SEXP C, SEXP zz, SEXP n_, SEXP s_, SEXP wSave_) {
@@ -142,6 +152,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_mrtsrcpp_predict0", (DL_FUNC)&_autoFRK_mrtsrcpp_predict0, 4},
     {"_autoFRK_mrtsrcpp_predict", (DL_FUNC)&_autoFRK_mrtsrcpp_predict, 7},
     {"_autoFRK_gram_stats", (DL_FUNC)&_autoFRK_gram_stats, 2},
+    {"_autoFRK_getHalf_stats", (DL_FUNC)&_autoFRK_getHalf_stats, 1},
     {"_autoFRK_cMLEimat_stats", (DL_FUNC)&_autoFRK_cMLEimat_stats, 6},
     {NULL, NULL, 0}};
 
