@@ -283,6 +283,14 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         const char* e = std::getenv("FRK_GRAM_PATH");
         return e && std::string(e) == "cpasync";
     }();
+    static const bool force_wide = [] {
+        const char* e = std::getenv("FRK_GRAM_PATH");
+        return e && (std::string(e) == "cpasync" || std::string(e) == "tma");
+    }();
+    if (!force_wide && gram_stats_narrow_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st)) {
+        ws.launches += 3;
+        return;
+    }
     GramLayout lay;
     if (!force_cpasync && gram_tma_usable(dF, ldf, dZ, T, ldz, n)) {
         gram_stats_tma_dev(dF, n, K, ldf, dZ, T, ldz, dw, ws, sms, lay, st);

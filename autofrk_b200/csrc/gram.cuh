@@ -30,4 +30,8 @@ bool gram_tma_usable(const double* dF, int64_t ldf, const double* dZ, int T, int
 void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
                         const double* dw, GramWorkspace& ws, int sms, GramLayout& lay, cudaStream_t st);
 
+// narrow variant (gram_narrow.cu) for K <= 48, T <= 16: returns false if it does not apply
+bool gram_stats_narrow_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
+                           const double* dw, double* dpacked, GramWorkspace& ws, int sms, int nzz, cudaStream_t st);
+
 }  // namespace frk

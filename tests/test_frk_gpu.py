@@ -367,3 +367,35 @@ def test_knn_imputation_and_autoFRK_with_missing_values():
 def _frk_error():
     from autofrk_b200._lib import FrkError
     return FrkError
+
+
+@pytest.mark.parametrize("n,K,T,weighted", [(100_003, 32, 4, False), (50_000, 5, 1, True), (77_777, 48, 8, False),
+                                             (20_001, 17, 0, False), (64_000, 40, 16, True), (999, 3, 2, False)])
+def test_gram_narrow_variant(n, K, T, weighted):
+    """few basis functions: the register-tile kernel (gram_narrow.cu) through the device entry point."""
+    import ctypes as C
+    import torch
+    from autofrk_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ld = n + (n & 1)
+    F = torch.randn((K, ld), dtype=torch.float64, device="cuda", generator=g).T[:n]
+    Z = torch.randn((max(T, 1), ld), dtype=torch.float64, device="cuda", generator=g).T[:n]
+    w = (torch.rand(ld, dtype=torch.float64, device="cuda", generator=g) + 0.5) if weighted else None
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    packed = torch.full((plen,), float("nan"), dtype=torch.float64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, ld, C.c_void_p(Z.data_ptr()), T, ld,
+                                           None if w is None else C.c_void_p(w.data_ptr()), C.c_void_p(packed.data_ptr()), st))
+    torch.cuda.synchronize()
+    Fh, Zh = F.cpu().numpy(), Z.cpu().numpy()
+    wh = np.ones(n) if w is None else w[:n].cpu().numpy()
+    G = packed[:K * K].cpu().numpy().reshape(K, K, order="F")
+    assert relmax(G, Fh.T @ (wh[:, None] * Fh)) < 1e-12 and np.array_equal(G, G.T)
+    if T:
+        Cm = packed[K * K:K * K + K * T].cpu().numpy().reshape(K, T, order="F")
+        assert relmax(Cm, Fh.T @ (wh[:, None] * Zh[:, :T])) < 1e-12
+        zz = np.sum(wh[:, None] * Zh[:, :T] ** 2)
+        assert abs(packed[-1].item() - zz) / zz < 1e-12
+    else:
+        assert packed[-1].item() == 0.0
