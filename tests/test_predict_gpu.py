@@ -147,3 +147,33 @@ def test_predict_dev_torch_and_linearity():
     torch.cuda.synchronize()
     assert torch.equal(out2, out * 2.0)
     assert plan.launches > 0
+
+
+def test_output_guard_bands_untouched():
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted with guard bands: a padded
+    leading dimension and spare columns pre-filled with a sentinel must survive every K1 configuration."""
+    import torch
+    from autofrk_b200 import mrts as G
+    from autofrk_b200._lib import FRK_OUT_BASIS
+
+    rng = np.random.default_rng(12)
+    sentinel = -7.25
+    for d, m, kstar, n2 in [(2, 90, 28, 1001), (2, 400, 197, 3333), (2, 700, 497, 2047), (3, 300, 600, 1500), (1, 50, 9, 77)]:
+        Xu = rng.random((m, d))
+        UZ = np.zeros((m + d + 1, kstar + d + 1))
+        UZ[:m, :kstar] = rng.standard_normal((m, kstar))
+        K = kstar + d + 1
+        plan = G.MrtsPlan(Xu, rng.standard_normal((d + 1, m)), UZ, np.ones(d), K)
+        ld = n2 + 37
+        xfull = torch.rand((d, ld), dtype=torch.float64, device="cuda")
+        x = xfull.T[:n2]                                      # input with its own padded leading dimension
+        buf = torch.full((K + 2, ld), sentinel, dtype=torch.float64, device="cuda")
+        out = buf.T[:n2, 1:K + 1]                             # n2 x K window: guard rows below, guard columns on both sides
+        for mode in (0, FRK_OUT_BASIS):
+            buf.fill_(sentinel)
+            plan.predict_dev(x, out, mode=mode)
+            torch.cuda.synchronize()
+            full = buf.T
+            assert torch.all(full[n2:, :] == sentinel), (d, m, kstar, mode, "rows past n2 written")
+            assert torch.all(full[:, 0] == sentinel) and torch.all(full[:, K + 1] == sentinel), "guard columns written"
+            assert not torch.any(full[:n2, 1:K + 1] == sentinel)
