@@ -192,6 +192,8 @@ static void predict_cols(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t l
     const PredictKernelInfo* ki = p->ki;
     const int64_t ntiles = (n2 + ki->bm - 1) / ki->bm;
     const int grid = int(std::min<int64_t>(ntiles, p->sm_count));
+    if (((ntiles + grid - 1) / grid) * int64_t(p->nchunks) >= (int64_t(1) << 31))
+        fail(1, "xnew has too many rows for one launch (%lld): evaluate it in row blocks", (long long)n2);
     for (auto& sl : p->slices) {
         const int ncols = std::min(sl.ncols, kc - sl.col0);
         if (ncols <= 0) break;

@@ -279,11 +279,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     uint32_t ppar = 0;
     int cphi = AHEAD % nchunks;            // chunk (within its tile) whose Phi is produced this iteration
     int cref = NSTAGE % nchunks;           // chunk that refills the stage released this iteration
-    int64_t left = total;                  // iterations still to run, including this one
+    int left = int(total);                 // iterations still to run, including this one (host checks < 2^31)
     bool okp = false, okw = false;         // early (non-blocking) probes of this iteration's barriers
     for (int64_t til = 0; til < ntl; ++til) {
         const int64_t tile = blockIdx.x + til * gridDim.x;
         const int xb = int(til & 1);
+        // Phi of the tile's first chunk complete: every warp has finished iteration it - AHEAD, hence nobody reads
+        // the previous tile's rows any more -> stage the next tile's (kept out of the chunk loop)
+        if (!okp) mbar_wait(&phi_full[pb], ppar);
+        okp = true;
+        if (til + 1 < ntl) load_xs(xb ^ 1, tile + gridDim.x);
         // accumulators start at -[1, x] * Cpoly   (src/autoFRK.cpp:317-324)
         double acc[MT][NT][2];
         {
@@ -310,8 +315,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
         for (int c = 0; c < nchunks; ++c) {
             // (1) Phi of THIS chunk complete: every warp has finished iteration it - AHEAD
             if (!okp) mbar_wait(&phi_full[pb], ppar);
-            //     ... hence nobody reads the previous tile's rows any more: stage the next tile's
-            if (c == 0 && til + 1 < ntl) load_xs(xb ^ 1, tile + gridDim.x);
             // (2) inputs of the Phi chunk produced in this iteration (rows from shared, knots prefetched)
             const bool more = (left > AHEAD);
             // without prefetch: knots of the Phi chunk produced now; with: those of the next iteration's
