@@ -131,15 +131,6 @@ __device__ __forceinline__ uint32_t smem_add_relaxed(uint32_t* p, uint32_t v) {
     asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
-// fire-and-forget increment of a shared counter (no result, nothing to wait for)
-__device__ __forceinline__ void smem_red_add(uint32_t* p, uint32_t v) {
-    asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t smem_ld_volatile(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
 // global -> shared bulk copy through the TMA unit, completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                              uint64_t* bar) {

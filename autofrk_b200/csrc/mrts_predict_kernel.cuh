@@ -445,10 +445,10 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
 // <D, WR, WC, MT, NT, KC, NSTAGE>: KC chosen so that every thread evaluates a whole number of Phi
 // values per chunk (BM*KC is a multiple of the thread count)
 #define FRK_PREDICT_CONFIG_TABLE(D)                                                                        \
-    predict_info<PredictCfg<D, 4, 4, 4, 1, 8, 4>>(),   /* BM 128, BN  32, 2 Phi/thread */                  \
-    predict_info<PredictCfg<D, 4, 4, 4, 2, 8, 4>>(),   /* BM 128, BN  64 */                                \
-    predict_info<PredictCfg<D, 4, 4, 4, 3, 8, 4>>(),   /* BM 128, BN  96 */                                \
-    predict_info<PredictCfg<D, 4, 4, 4, 4, 8, 4>>(),   /* BM 128, BN 128 */                                \
+    predict_info<PredictCfg<D, 4, 4, 4, 1, 32, 4>>(),  /* BM 128, BN  32, 8 Phi/thread */                  \
+    predict_info<PredictCfg<D, 4, 4, 4, 2, 32, 4>>(),  /* BM 128, BN  64 */                                \
+    predict_info<PredictCfg<D, 4, 4, 4, 3, 16, 4>>(),  /* BM 128, BN  96 */                                \
+    predict_info<PredictCfg<D, 4, 4, 4, 4, 16, 4>>(),  /* BM 128, BN 128 */                                \
     predict_info<PredictCfg<D, 2, 8, 4, 3, 16, 4>>(),  /* BM  64, BN 192, 2 Phi/thread */                  \
     predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>(),  /* BM  96, BN 200, 4 Phi/thread, 15 warps */        \
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
