@@ -159,3 +159,72 @@ def test_golden_vectors():
         assert relmax(fit["nconst"], gold[f"{tag}_nconst"]) < 1e-14
         X1 = O.mrtsrcpp_predict(Xu, None, xnew, gold[f"{tag}_BBBH"], gold[f"{tag}_UZ"], gold[f"{tag}_nconst"], kstar)["X1"]
         assert colrel(X1, gold[f"{tag}_X1"]) < 1e-12
+
+
+def test_fit_restatement_against_50_digit_arithmetic():
+    """the whole C++ mrts() (src/autoFRK.cpp:160-217) and the projection (:316-324) re-evaluated with 50-digit mpmath
+    (kernel matrix, normal equations, double centering, symmetric eigensolve, gammas, BBBH, X1) on a tiny problem."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    rng = np.random.default_rng(42)
+    for d, m, k in [(2, 12, 5), (3, 11, 4), (1, 10, 3)]:
+        Xu = rng.random((m, d))
+        xd = xobs_diag_of(Xu, m)
+        fit = O.mrtsrcpp(Xu, xd, k)
+        X = [[mp.mpf(float(v)) for v in row] for row in Xu]
+
+        def phi(a, b):
+            r = mp.sqrt(sum((a[c] - b[c]) ** 2 for c in range(d)))
+            if d == 1:
+                return r ** 3 / 12
+            if d == 2:
+                return mp.mpf(0) if r == 0 else r * r * mp.log(r) / (8 * mp.pi)
+            return -r / 8
+
+        H = mp.matrix(m, m)
+        for i in range(m):
+            for j in range(m):
+                H[i, j] = mp.mpf(0) if i == j else phi(X[i], X[j])
+        B = mp.matrix(m, d + 1)
+        for i in range(m):
+            B[i, 0] = 1
+            for c in range(d):
+                B[i, c + 1] = X[i][c]
+        BBB = mp.inverse(B.T * B) * B.T
+        AH = H - (H * B) * BBB
+        AHA = AH - BBB.T * (B.T * AH)
+        AHA = (AHA + AHA.T) / 2
+        ev, EV = mp.eigsy(AHA)
+        order = sorted(range(m), key=lambda i: -ev[i])[:k]
+        root = mp.sqrt(m)
+        gam = mp.matrix(m, k)
+        for c, idx in enumerate(order):
+            col = [EV[i, idx] for i in range(m)]
+            big = max(range(m), key=lambda i: abs(col[i]))
+            sgn = 1 if col[big] > 0 else -1                       # the oracle's sign convention (fix_signs)
+            for i in range(m):
+                gam[i, c] = sgn * col[i]
+        rho = [ev[idx] for idx in order]
+        gammas = gam - B * (BBB * gam)
+        for c in range(k):
+            for i in range(m):
+                gammas[i, c] = gammas[i, c] / rho[c] * root
+        BBBH = BBB * H
+        to_np = lambda M: np.array([[float(M[i, j]) for j in range(M.cols)] for i in range(M.rows)])
+        assert colrel(fit["X"][:, d + 1:], to_np(gam) * float(root)) < 1e-11
+        assert colrel(fit["UZ"][:m, :k], to_np(gammas)) < 1e-10
+        assert colrel(fit["BBBH"].T, to_np(BBBH).T) < 1e-11
+        # projection at new points
+        xn = rng.random((7, d))
+        ref = O.mrtsrcpp_predict(Xu, xd, xn, fit["BBBH"], fit["UZ"], fit["nconst"], k)["X1"]
+        Pn = mp.matrix(7, m)
+        Bn = mp.matrix(7, d + 1)
+        for i in range(7):
+            xi = [mp.mpf(float(v)) for v in xn[i]]
+            Bn[i, 0] = 1
+            for c in range(d):
+                Bn[i, c + 1] = xi[c]
+            for j in range(m):
+                Pn[i, j] = phi(xi, X[j])
+        X1 = Pn * gammas - Bn * (BBBH * gammas)
+        assert colrel(ref, to_np(X1)) < 1e-9
