@@ -376,7 +376,7 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
         rng = np.random.default_rng(0)
         loc = rng.random((2000, 2))
         z = (3.0 * np.sin(4 * loc[:, 0]) * np.cos(3 * loc[:, 1]) + rng.standard_normal(2000)).reshape(-1, 1)
-        GF.autoFRK(z, loc, maxK=20)                                    # warm-up
+        GF.autoFRK(z, loc)                                             # warm-up (cuSOLVER workspaces at these sizes)
         t0 = time.perf_counter()
         got = GF.autoFRK(z, loc)
         t_gpu = time.perf_counter() - t0
