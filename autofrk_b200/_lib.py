@@ -42,6 +42,7 @@ _SIGNATURES = {
     "frk_version": (_i32, []),
     "frk_device_count": (_i32, [C.POINTER(_i32)]),
     "frk_set_device": (_i32, [_i32]),
+    "frk_release_cached_memory": (_i32, []),
     "frk_mrtsrcpp_predict": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _vp, _i64, _i64,
                                     _vp, _i64, _i32, _vp]),
     "frk_mrtsrcpp": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "frk_gram_packed_len": (_i64, [_i32, _i32]),
     "frk_gram_stats_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp]),
     "frk_plan_predict_gram_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _i64, _vp]),
+    "frk_peer_sum_dev": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "frk_getHalf": (_i32, [_vp, _i64, _i32, _vp]),
     "frk_cMLEimat_stats": (_i32, [_vp, _i64, _vp, _i64, C.c_double, _i32, _i32, _i64, C.c_double, _i32, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _vp]),

@@ -130,6 +130,10 @@ int32_t frk_device_count(int32_t* count) {
     });
 }
 
+int32_t frk_release_cached_memory(void) {
+    return guarded([&] { frk::pool_release_all(); });
+}
+
 int32_t frk_set_device(int32_t device) {
     return guarded([&] {
         require_device();

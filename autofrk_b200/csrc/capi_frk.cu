@@ -32,6 +32,19 @@ __global__ void rowdot_sqrt_kernel(const double* __restrict__ FV, const double* 
     se[i] = sqrt(fmax(0.0, s));
 }
 
+// One-shot all-reduce over NVLink peer memory: every rank reads every rank's packed statistics straight from the
+// peers' HBM (P2P loads through NVSwitch) and adds them in rank order, so all ranks obtain bitwise-identical sums.
+struct PeerPtrs {
+    const double* p[16];
+};
+__global__ void peer_sum_kernel(const PeerPtrs ptrs, int nranks, int64_t len, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < nranks; ++r) s += __ldcv(ptrs.p[r] + i);   // .cv: never served from a stale cache line
+        out[i] = s;
+    }
+}
+
 int64_t default_chunk_rows(const frk::MrtsPlan* mp, int K) {
     const int64_t bm = mp->ki ? mp->ki->bm : 128;
     const int64_t wave = bm * mp->sm_count;
@@ -150,6 +163,18 @@ int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t 
         if (ldx < n2 || (T > 0 && ldz < n2)) frk::fail(FRK_EINVAL, "leading dimensions must be >= n2");
         predict_gram(plan, d_xnew, n2, ldx, d_Z, T, ldz, d_weights, d_packed, chunk_rows,
                      static_cast<cudaStream_t>(stream));
+    });
+}
+
+int32_t frk_peer_sum_dev(const void* const* d_ptrs, int32_t nranks, int64_t len, double* d_out, void* stream) {
+    return guarded([&] {
+        if (nranks < 1 || nranks > 16) frk::fail(FRK_EINVAL, "peer sum supports 1..16 ranks (one NVSwitch node)");
+        if (len < 1) return;
+        PeerPtrs pp;
+        for (int r = 0; r < 16; ++r) pp.p[r] = (r < nranks) ? static_cast<const double*>(d_ptrs[r]) : nullptr;
+        const int grid = int(std::min<int64_t>((len + 255) / 256, 592));
+        peer_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pp, nranks, len, d_out);
+        FRK_CUDA(cudaGetLastError());
     });
 }
 

@@ -35,7 +35,14 @@ struct Error : std::runtime_error {
                         __LINE__, #expr);                                                        \
     } while (0)
 
-// RAII device buffer (cudaMallocAsync-free: plain cudaMalloc keeps the library usable without a pool)
+// Size-class cache for device allocations (per host thread and device).  cudaMalloc / cudaFree synchronise the device
+// and become very slow once peer mappings exist (symmetric memory, NCCL), while the K x K stages allocate dozens of
+// small temporaries per call; cached blocks are reused across calls and released by frk_release_cached_memory().
+void* pool_alloc(size_t bytes);
+void pool_free(void* p, size_t bytes);
+void pool_release_all();
+
+// RAII device buffer backed by the cache
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -53,10 +60,10 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) FRK_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (count) p = static_cast<T*>(pool_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p, n * sizeof(T));
         p = nullptr;
         n = 0;
     }

@@ -78,14 +78,42 @@ def broadcast_fit(fit: dict | None, src: int = 0) -> dict:
     return out
 
 
-def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0, w_t=None):
+class PeerAllReduce:
+    """The fit's single collective as our own kernel over NVLink peer memory (frk_peer_sum_dev): the packed statistics
+    live in a symmetric-memory allocation, every rank reads all peers' buffers with P2P loads and adds them in rank
+    order.  torch's symmetric memory provides the allocation, the peer mappings and the device-side barriers."""
+
+    def __init__(self, length: int, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.length = int(length)
+        self.buf = symm.empty(self.length, dtype=torch.float64, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.out = torch.empty(self.length, dtype=torch.float64, device=device)
+        self.world = self.hdl.world_size
+        self._ptrs = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in self.hdl.buffer_ptrs])
+
+    def __call__(self):
+        """`self.buf` holds this rank's statistics (written on the current stream); returns the sum over ranks."""
+        import torch
+
+        self.hdl.barrier(channel=0)                                # every rank's statistics are complete and visible
+        st = C.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)
+        check(lib.frk_peer_sum_dev(self._ptrs, self.world, self.length, C.c_void_p(self.out.data_ptr()), st))
+        self.hdl.barrier(channel=1)                                # peers are done reading before the next overwrite
+        return self.out
+
+
+def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0, w_t=None, out=None):
     """packed statistics of this rank's rows, basis never materialised (frk_plan_predict_gram_dev)."""
     import torch
 
     n2, d = x_t.shape
     T = 0 if Z_t is None else Z_t.shape[1]
     K = plan.k
-    packed = torch.empty(lib.frk_gram_packed_len(K, T), dtype=torch.float64, device=x_t.device)
+    packed = out if out is not None else torch.empty(lib.frk_gram_packed_len(K, T), dtype=torch.float64, device=x_t.device)
     ldx = x_t.stride(1) if d > 1 else n2
     ldz = (Z_t.stride(1) if T > 1 else n2) if T else n2
     st = C.c_void_p(torch.cuda.current_stream(x_t.device).cuda_stream)
@@ -96,15 +124,20 @@ def predict_gram_shard(plan, x_t, Z_t, chunk_rows: int = 0, w_t=None):
     return packed
 
 
-def fit_sharded(plan, x_t, Z_t, n_total: int, s: float = 0.0, wSave: bool = True, chunk_rows: int = 0):
-    """cMLEimat over row shards: local fused predict->Gram, ONE all-reduce, replicated K x K stage.
-    Returns the same list as cMLEimat (R/autoFRK.R:399-480)."""
+def fit_sharded(plan, x_t, Z_t, n_total: int, s: float = 0.0, wSave: bool = True, chunk_rows: int = 0, peer=None):
+    """cMLEimat over row shards: local fused predict->Gram, ONE collective, replicated K x K stage.
+    `peer` (a PeerAllReduce of the right length) runs the collective as our own NVLink peer-memory kernel;
+    otherwise it is one NCCL all-reduce.  Returns the same list as cMLEimat (R/autoFRK.R:399-480)."""
     import torch
 
     from .frk import cmle_from_stats
 
     K, T = plan.k, Z_t.shape[1]
-    packed = allreduce_stats(predict_gram_shard(plan, x_t, Z_t, chunk_rows))
+    if peer is not None:
+        predict_gram_shard(plan, x_t, Z_t, chunk_rows, out=peer.buf)
+        packed = peer()
+    else:
+        packed = allreduce_stats(predict_gram_shard(plan, x_t, Z_t, chunk_rows))
     torch.cuda.current_stream().synchronize()
     zz = float(packed[-1].item())
     G = packed[:K * K]

@@ -349,15 +349,23 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
     Z = torch.randn((T, rows), dtype=torch.float64, device="cuda", generator=gen).T
     xs = x[:rows]
     D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True)       # warm-up (workspaces, cuSOLVER handles)
+    peer = None
+    if world > 1:
+        try:   # the collective as our own NVLink peer-memory kernel (falls back to NCCL if symmetric memory is unavailable)
+            from autofrk_b200._lib import lib as _l
+            peer = D.PeerAllReduce(_l.frk_gram_packed_len(K, T), xs.device)
+            D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True, peer=peer)
+        except Exception:
+            peer = None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t0 = time.perf_counter()
     e0.record()
-    packed = D.predict_gram_shard(plan, xs, Z)
+    packed = D.predict_gram_shard(plan, xs, Z, out=None if peer is None else peer.buf)
     e1.record()
-    D.allreduce_stats(packed)
+    packed = peer() if peer is not None else D.allreduce_stats(packed)
     e2.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -369,6 +377,8 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
     out["cmle_sharded"] = {
         "rows_per_gpu": rows, "K": K, "T": T, "predict_gram_ms": e0.elapsed_time(e1), "allreduce_ms": e1.elapsed_time(e2),
         "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
+        "collective": "none (1 GPU)" if world == 1 else ("frk_peer_sum_dev over NVLink peer memory" if peer is not None
+                                                        else "NCCL all_reduce"),
         "note": "predict_gram = K1 (basis on the fly, 2 GB chunks) + K4 (Gram/cross-products); credited Gram flops "
                 f"{gram_flops:.3e} per GPU"}
     if rank == 0:
@@ -388,6 +398,14 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
             ref = O.autoFRK(z, loc)
             out["autoFRK_config0"]["cpu_oracle_wall_s"] = time.perf_counter() - t0
             out["autoFRK_config0"]["same_K"] = bool(ref["G"].X.shape[1] == got["G"].X.shape[1])
+            try:   # small dense eigenproblems often run faster on ONE BLAS thread: report that too
+                from threadpoolctl import threadpool_limits
+                with threadpool_limits(limits=1):
+                    t0 = time.perf_counter()
+                    O.autoFRK(z, loc)
+                    out["autoFRK_config0"]["cpu_oracle_wall_s_1thread"] = time.perf_counter() - t0
+            except Exception:
+                pass
     return out
 
 

@@ -37,6 +37,8 @@ const char* frk_last_error(void);
 int32_t frk_version(void);
 int32_t frk_device_count(int32_t* count);
 int32_t frk_set_device(int32_t device);
+/* device temporaries are cached between calls; this returns the cached blocks to the driver */
+int32_t frk_release_cached_memory(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Reference boundary, one function per registered `.Call` routine (src/RcppExports.cpp:71-77).
@@ -123,6 +125,12 @@ int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf,
 int32_t frk_plan_predict_gram_dev(frk_plan* plan, const double* d_xnew, int64_t n2, int64_t ldx, const double* d_Z,
                                   int32_t T, int64_t ldz, const double* d_weights, double* d_packed,
                                   int64_t chunk_rows, void* stream);
+
+/* Multi-GPU combine step of the fit, as one kernel over NVLink peer memory instead of a library all-reduce:
+ * d_ptrs[r] is rank r's packed statistics buffer mapped into THIS device's address space (symmetric memory /
+ * CUDA IPC); d_out[i] = sum_r d_ptrs[r][i], added in rank order on every rank (bitwise-identical results).
+ * The caller orders it after every rank's frk_gram_stats_dev (a device-side barrier over the same allocation). */
+int32_t frk_peer_sum_dev(const void* const* d_ptrs, int32_t nranks, int64_t len, double* d_out, void* stream);
 
 /* getHalf (R/helper.R:19-26) given G = t(Fk) %*% iDFk (K x K, ld ldg, lower triangle read): half = G^(-1/2),
  * zero eigenvalues -> 0. */

@@ -31,6 +31,22 @@ def main():
     x, Z = x_all[:, r0:r1].contiguous().T, z_all[:, r0:r1].contiguous().T
     out = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True)
     res = {}
+    peer_ok, peer_err = None, ""
+    try:   # the same collective as our own kernel over NVLink peer memory
+        from autofrk_b200 import _lib
+        peer = D.PeerAllReduce(_lib.lib.frk_gram_packed_len(K, T), x.device)
+        outp = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True, peer=peer)
+        outp2 = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True, peer=peer)      # buffer reuse
+        relp = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+        peer_ok = bool(relp(outp["M"], out["M"]) < 1e-12 and relp(outp["w"], out["w"]) < 1e-12
+                       and np.array_equal(outp2["M"], outp["M"]))
+        # every rank must hold bitwise-identical sums
+        chk = torch.tensor(np.ascontiguousarray(outp["M"])).cuda()
+        ref0 = chk.clone()
+        dist.broadcast(ref0, src=0)
+        peer_ok = peer_ok and bool(torch.equal(chk, ref0))
+    except Exception as e:  # pragma: no cover
+        peer_err = repr(e)[:300]
     if rank == 0:
         # single-GPU reference of the same call (world-size-independent path)
         dist_initialized = True
@@ -43,6 +59,8 @@ def main():
         res = dict(world=world, v=[out["v"], ref["v"]], dM=rel(out["M"], ref["M"]), dw=rel(out["w"], ref["w"]),
                    dV=rel(out["V"], ref["V"]), dnll=abs(out["negloglik"] - ref["negloglik"]) / abs(ref["negloglik"]))
         res["ok"] = bool(res["dM"] < 1e-10 and res["dw"] < 1e-10 and res["dV"] < 1e-10 and res["dnll"] < 1e-12)
+        res["peer_allreduce_ok"] = peer_ok
+        res["peer_err"] = peer_err
         print(json.dumps(res))
     dist.barrier()
     dist.destroy_process_group()
