@@ -1,11 +1,11 @@
 """Row-sharded multi-GPU driver: one process per GPU (torchrun), torch.distributed for the plumbing.
 
 The hot path shards by rows (locations are independent): knots / eigenvectors / Cpoly are replicated,
-basis evaluation needs no collective at all, and the fit needs exactly one -- an all-reduce(SUM) of the
-packed sufficient statistics [G (K*K) | C (K*T) | zz] (2.4 MB at K=500, T=100), after which the K x K
-stage runs replicated on every rank.  The payload is latency-bound on NVLink 5 (tens of microseconds
-against >= 0.1 s of compute per shard), so NCCL's all-reduce is used as is; a one-shot multimem
-all-reduce fused into the Gram epilogue would save nothing measurable ("Multi-GPU").
+basis evaluation needs no collective at all, and the fit needs exactly one -- the sum of the packed
+sufficient statistics [G (K*K) | C (K*T) | zz] (2.4 MB at K=500, T=100), after which the K x K stage runs
+replicated on every rank.  The sum runs as our own kernel over NVLink peer memory (PeerAllReduce ->
+frk_peer_sum_dev: symmetric-memory buffers, P2P loads, rank-ordered addition, bitwise-identical on all
+ranks); NCCL's all-reduce (allreduce_stats) is the fallback.
 """
 from __future__ import annotations
 
