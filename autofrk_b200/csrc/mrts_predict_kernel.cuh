@@ -157,7 +157,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     constexpr int D = C::D, DP = C::DP, BM = C::BM, BN = C::BN, KC = C::KC, KQ = C::KQ;
     constexpr int MT = C::MT, NT = C::NT, NSTAGE = C::NSTAGE, NTHREADS = C::NTHREADS, VPT = C::VPT;
     constexpr int NPB = C::NPB, NWARPS = C::NWARPS, AHEAD = C::AHEAD;
-    constexpr int PHI_Q = (KQ >= 3) ? 1 : 0;  // k4-group after which the Phi arithmetic is placed in the source
+#ifdef FRK_PHI_Q   // tuning aid: where in the DMMA block the Phi arithmetic is placed in the source
+    constexpr int PHI_Q = (FRK_PHI_Q < KQ) ? FRK_PHI_Q : KQ - 1;
+#else
+    constexpr int PHI_Q = 0;  // k4-group after which the Phi arithmetic is placed in the source (ptxas spreads it anyway)
+#endif
     constexpr bool PREFETCH = (VPT <= 2);     // knots one iteration early in registers (if they are affordable)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
