@@ -82,6 +82,23 @@ extern "C" {
 
 int64_t frk_gram_packed_len(int32_t K, int32_t T) { return int64_t(frk::gram_packed_len(K, T)); }
 
+int64_t frk_gram_job_plan(int32_t K, int32_t T, int32_t* njobs, int32_t* triples, int64_t cap) {
+    if (K < 1 || T < 0) return -1;
+    const std::vector<frk::GramJobHost> jobs = frk::gram_pack_jobs(K, T);
+    if (njobs) *njobs = int32_t(jobs.size());
+    int64_t count = 0;
+    for (size_t j = 0; j < jobs.size(); ++j)
+        for (const auto& ab : jobs[j].tiles) {
+            if (triples && count < cap) {
+                triples[3 * count + 0] = int32_t(j);
+                triples[3 * count + 1] = ab.first;
+                triples[3 * count + 2] = ab.second;
+            }
+            ++count;
+        }
+    return count;
+}
+
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
                            int64_t ldz, const double* d_weights, double* d_packed, void* stream) {
     return guarded([&] {

@@ -291,10 +291,12 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         ws.launches += 3;
         return;
     }
-    GramLayout lay;
     if (!force_cpasync && gram_tma_usable(dF, ldf, dZ, T, ldz, n)) {
-        gram_stats_tma_dev(dF, n, K, ldf, dZ, T, ldz, dw, ws, sms, lay, st);
-    } else {
+        gram_stats_tma_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st);
+        ws.launches += 3;
+        return;
+    }
+    {
         GramArgs a;
         a.F = dF; a.ldf = ldf; a.K = K;
         a.Z = dZ; a.ldz = ldz; a.T = T;
@@ -334,14 +336,13 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         else if (aligned) gram_kernel<true, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
         else gram_kernel<false, true><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
         FRK_CUDA(cudaGetLastError());
-        lay.ntf = a.ntf; lay.ntz = a.ntz; lay.npairs = a.npairs; lay.nsplit = a.nsplit;
+        gram_reduce_kernel<<<a.npairs, 256, 0, st>>>(ws.partial.p, a.nsplit, a.npairs, a.ntf, a.ntz, K, T, ws.zzpart.p, nzz,
+                                                     dpacked);
+        FRK_CUDA(cudaGetLastError());
+        ws.last_nsplit = a.nsplit;
+        ws.last_npairs = a.npairs;
     }
-    gram_reduce_kernel<<<lay.npairs, 256, 0, st>>>(ws.partial.p, lay.nsplit, lay.npairs, lay.ntf, lay.ntz, K, T, ws.zzpart.p,
-                                                   nzz, dpacked);
-    FRK_CUDA(cudaGetLastError());
     ws.launches += 3;
-    ws.last_nsplit = lay.nsplit;
-    ws.last_npairs = lay.npairs;
 }
 
 }  // namespace frk

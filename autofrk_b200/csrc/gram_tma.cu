@@ -1,17 +1,29 @@
-// K4, TMA variant: G = F' W F, C = F' W Z over 128 x 128 output tiles, operands staged by 2-D TMA tensor copies.
+// K4, TMA variant: G = F' W F, C = F' W Z from 32 x 32 warp tiles packed into jobs, operands staged by 2-D TMA copies.
 //
-// Same mathematics and the same workspace / reduction as gram.cu (which stays as the path for odd leading
-// dimensions); what changes is the machinery around the DMMAs, applying what the K1 profiles taught:
-//   * panels arrive by cp.async.bulk.tensor.2d (UTMALDG) with SWIZZLE_128B into dense [column][16 rows] boxes;
+// Same mathematics as gram.cu (which stays as the path for odd leading dimensions); what changes is the machinery
+// around the DMMAs, applying what the K1 profiles taught:
+//   * the output is cut into 32-column blocks (F blocks, then Z blocks); the work is the list of block pairs
+//     (a <= b) of G plus the F x Z pairs, one 32 x 32 register tile per warp.  A job is up to 16 such tiles that
+//     together touch at most 8 column blocks ("slots"); the host packs the pairs into jobs (4 x 4 macro tiles,
+//     then the under-filled ones merged: a diagonal macro tile's 10 upper-triangular tiles share a job with the
+//     F x Z tiles of the same blocks), so no DMMA is spent on a lower triangle or on padding beyond 31 columns.
+//     The 128-column tiling this replaces spent 200 warp tiles on K = 500, T = 1 (now 152) and 68 on K = 200,
+//     T = 20 (now 35);
+//   * a job with <= 8 (<= 4) tiles runs every tile on 2 (4) warps that take alternate k4-steps, so small shapes
+//     still occupy all four SM sub-partitions; the reduction adds those partials like further row splits;
+//   * slots arrive by cp.async.bulk.tensor.2d (UTMALDG) with SWIZZLE_128B into dense [column][16 rows] boxes;
 //     the MMA k index is permuted (rows 2q, 2q+1, 2q+8, 2q+9 form k4-step q) so that every fragment LDS.64 is
 //     bank-conflict free under that swizzle; out-of-range rows / columns are zero-filled by the TMA unit;
 //   * no CTA-wide barrier inside a work item: a 6-deep stage ring, `full` mbarriers, and the warp that is last
-//     to finish with a stage (shared counter) re-arms it;
-//   * persistent CTAs pull (row split, tile pair) items from a global counter, split-major so that CTAs running
-//     together read the same rows of F through L2;
-//   * diagonal tile pairs run only their 10 upper-triangular 32 x 32 warp tiles, on warps 0..9 (3,3,2,2 per SM
-//     sub-partition), so a diagonal item costs 3/4 of an off-diagonal one instead of the same.
+//     to finish with a stage (shared counter) re-arms it, one TMA per lane;
+//   * persistent CTAs pull (row split, job) items from a global counter, split-major so that CTAs running
+//     together read the same rows of F through L2; jobs are ordered longest first;
+//   * every item writes its tiles to a workspace and a second kernel adds them in a fixed order (bitwise
+//     reproducible, no atomics) and mirrors G.
 #include <algorithm>
+#include <cstdlib>
+#include <iterator>
+#include <type_traits>
 #include <vector>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -22,25 +34,35 @@ namespace frk {
 
 namespace {
 
-constexpr int TB = 128;
-constexpr int KR = 16;
+constexpr int CB = 32;                            // columns per block = warp tile edge
+constexpr int KR = 16;                            // rows per pipeline stage
 constexpr int NST = 6;
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int PANEL_BYTES = TB * KR * 8;          // 16 KB, 1024-byte aligned (swizzle atom)
-constexpr int STAGE_BYTES = 2 * PANEL_BYTES;
+constexpr int MAXSLOTS = 8;
+constexpr int SLOT_BYTES = CB * KR * 8;           // 4 KB, 1024-byte aligned (swizzle atom)
+constexpr int STAGE_BYTES = MAXSLOTS * SLOT_BYTES;
+constexpr int TILE_DOUBLES = CB * CB;
 constexpr size_t SMEM_BYTES = size_t(NST) * STAGE_BYTES + 1024 /* alignment slack */ + 256;
 
+// one job: column blocks to stage (F blocks are < kb, Z blocks follow) and the block pairs computed from them
+struct GramJob {
+    int nslots, ntiles, kgroups;     // kgroups warps share a tile, taking alternate k4-steps
+    int slot_block[MAXSLOTS];
+    unsigned char slot_a[NWARPS], slot_b[NWARPS];
+    unsigned char ntn[NWARPS];       // 8-column groups of block b that hold real columns (1..4)
+};
+
 struct GramTmaArgs {
-    int K, T;
+    int K, T, kb;            // kb = number of 32-column blocks of F
     int64_t n;
     const double* w;
-    int ntf, ntz, npairs, nsplit;
-    int64_t rows_per_split;
-    double* partial;         // [nsplit][npairs][TB*TB]
+    int njobs, nsplit, nitems;
+    int nsplit_big;          // the first nsplit_big row splits hold rows_big rows each, the others rows_small
+    int64_t rows_big, rows_small;
+    double* partial;         // [nsplit][njobs][NWARPS][32*32], column-major tiles
     unsigned* counter;       // work-item counter (zeroed before the launch)
-    const int* pair_order;   // pair ids, long items first
-    int nitems;
+    const GramJob* jobs;     // longest first
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -53,10 +75,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 __device__ __forceinline__ void dmma_nv(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-
-// upper-triangular warp tiles of a diagonal 4 x 4 warp grid, in the order warps 0..9 take them
-__device__ __constant__ int kDiagWr[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
-__device__ __constant__ int kDiagWc[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -85,7 +103,6 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 
     int s = 0;           // ring position and parity carried across work items
     uint32_t par = 0;
-    const int nff = a.ntf * (a.ntf + 1) / 2;
 
     for (;;) {
         __syncthreads();  // every warp is done with the previous item (ring quiescent, done[] all zero)
@@ -93,43 +110,38 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         __syncthreads();
         const int item = *s_item;
         if (item >= a.nitems) break;
-        const int split = item / a.npairs;
-        const int pair = a.pair_order[item % a.npairs];
-        int ta = 0, tb = 0;
-        bool bz = false;
-        if (pair < nff) {
-            int p = pair;
-            for (ta = 0; ta < a.ntf; ++ta) {
-                const int cnt = a.ntf - ta;
-                if (p < cnt) { tb = ta + p; break; }
-                p -= cnt;
-            }
-        } else {
-            const int p = pair - nff;
-            ta = p / a.ntz;
-            tb = p % a.ntz;
-            bz = true;
-        }
-        const bool diag = (!bz && ta == tb);
-        const int nactive = diag ? 10 : NWARPS;
+        const int split = item / a.njobs;
+        const int jid = item % a.njobs;
+        const GramJob* const job = a.jobs + jid;
+        const int nslots = __ldg(&job->nslots);
+        const int ntiles = __ldg(&job->ntiles);
+        const int kgroups = __ldg(&job->kgroups);
+        const int nactive = ntiles * kgroups;
         const bool active = warp < nactive;
-        const int wr = diag ? kDiagWr[active ? warp : 0] : (warp >> 2);
-        const int wc = diag ? kDiagWc[active ? warp : 0] : (warp & 3);
-        const CUtensorMap* tmB = bz ? &tmZ : &tmF;
-        const uint32_t stage_tx = diag ? PANEL_BYTES : 2 * PANEL_BYTES;
+        const int tile = active ? warp % ntiles : 0;
+        const int kg = active ? warp / ntiles : 0;
+        const int sa = __ldg(&job->slot_a[tile]);
+        const int sb = __ldg(&job->slot_b[tile]);
+        const int ntn = __ldg(&job->ntn[tile]);
+        // the slot this lane copies when its warp re-arms a stage
+        const int my_block = (lane < nslots) ? __ldg(&job->slot_block[lane]) : 0;
+        const CUtensorMap* const my_tm = (my_block < a.kb) ? &tmF : &tmZ;
+        const int my_col = ((my_block < a.kb) ? my_block : my_block - a.kb) * CB;
+        const uint32_t stage_tx = uint32_t(nslots) * SLOT_BYTES;
 
-        const int64_t r_begin = int64_t(split) * a.rows_per_split;
-        const int64_t r_end = min(a.n, r_begin + a.rows_per_split);
+        const int64_t r_begin = (split < a.nsplit_big) ? int64_t(split) * a.rows_big
+                                                       : int64_t(a.nsplit_big) * a.rows_big + int64_t(split - a.nsplit_big) * a.rows_small;
+        const int64_t r_end = min(a.n, r_begin + ((split < a.nsplit_big) ? a.rows_big : a.rows_small));
         const int nsteps = (r_end > r_begin) ? int((r_end - r_begin + KR - 1) / KR) : 0;
 
-        auto issue = [&](int stage, int step) {  // one thread
+        auto issue = [&](int stage, int step) {  // one whole warp
             unsigned char* As = base + size_t(stage) * STAGE_BYTES;
             const int r0 = int(r_begin + int64_t(step) * KR);
-            mbar_expect_tx(&full[stage], stage_tx);
-            tma_load_2d(As, &tmF, r0, ta * TB, &full[stage]);
-            if (!diag) tma_load_2d(As + PANEL_BYTES, tmB, r0, tb * TB, &full[stage]);
+            if (lane == 0) mbar_expect_tx(&full[stage], stage_tx);
+            __syncwarp();
+            if (lane < nslots) tma_load_2d(As + lane * SLOT_BYTES, my_tm, r0, my_col, &full[stage]);
         };
-        if (tid == 0)
+        if (warp == 0)
             for (int i = 0; i < NST && i < nsteps; ++i) issue((s + i) % NST, i);
 
         double acc[4][4][2];
@@ -139,8 +151,8 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         if (active) {
-            const int a_line = (wr * 32 + g) * 128;
-            const int b_line = (wc * 32 + g) * 128;
+            const int a_line = sa * SLOT_BYTES + g * 128;
+            const int b_line = sb * SLOT_BYTES + g * 128;
             double wq[4] = {1.0, 1.0, 1.0, 1.0};
             auto load_w = [&](int step) {
 #pragma unroll
@@ -150,26 +162,18 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 }
             };
             if (WEIGHTED && nsteps > 0) load_w(0);
-            bool ok = false;
-            int ls = s;
-            uint32_t lpar = par;
-            for (int step = 0; step < nsteps; ++step) {
-                if (!ok) mbar_wait(&full[ls], lpar);
-                const unsigned char* As = base + size_t(ls) * STAGE_BYTES;
-                const unsigned char* Bs = diag ? As : As + PANEL_BYTES;
-                const int lsn = (ls + 1 == NST) ? 0 : ls + 1;
-                const uint32_t lparn = (ls + 1 == NST) ? (lpar ^ 1u) : lpar;
-                double wcur[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) wcur[q] = wq[q];
-                if (WEIGHTED && step + 1 < nsteps) load_w(step + 1);
+            double wcur[4];
+            // k4-steps q0, q0+dq, ... of one stage on the first NTN 8-column groups of block b
+            auto ksteps = [&](const unsigned char* As, auto ntn_c, int q0, int dq) {
+                constexpr int NTN = decltype(ntn_c)::value;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    double af[4], bf[4];
+                    if (dq != 1 && (q & (dq - 1)) != q0) continue;
+                    double af[4], bf[NTN];
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) af[mt] = *reinterpret_cast<const double*>(As + a_line + mt * 1024 + off[q]);
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) bf[nt] = *reinterpret_cast<const double*>(Bs + b_line + nt * 1024 + off[q]);
+                    for (int nt = 0; nt < NTN; ++nt) bf[nt] = *reinterpret_cast<const double*>(As + b_line + nt * 1024 + off[q]);
                     if (WEIGHTED) {
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt) af[mt] *= wcur[q];
@@ -177,15 +181,39 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) dmma_nv(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-                    if (q == 3 && step + 1 < nsteps) ok = mbar_test_wait(&full[lsn], lparn);
+                        for (int nt = 0; nt < NTN; ++nt) dmma_nv(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                }
+            };
+            bool ok = false;
+            int ls = s;
+            uint32_t lpar = par;
+            for (int step = 0; step < nsteps; ++step) {
+                if (!ok) mbar_wait(&full[ls], lpar);
+                const unsigned char* As = base + size_t(ls) * STAGE_BYTES;
+                const int lsn = (ls + 1 == NST) ? 0 : ls + 1;
+                const uint32_t lparn = (ls + 1 == NST) ? (lpar ^ 1u) : lpar;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wcur[q] = wq[q];
+                if (WEIGHTED && step + 1 < nsteps) load_w(step + 1);
+                if (kgroups == 1) {
+                    switch (ntn) {  // warp-uniform: real branches, never predicated-off DMMAs
+                        case 1: ksteps(As, std::integral_constant<int, 1>{}, 0, 1); break;
+                        case 2: ksteps(As, std::integral_constant<int, 2>{}, 0, 1); break;
+                        case 3: ksteps(As, std::integral_constant<int, 3>{}, 0, 1); break;
+                        default: ksteps(As, std::integral_constant<int, 4>{}, 0, 1); break;
+                    }
+                    if (step + 1 < nsteps) ok = mbar_test_wait(&full[lsn], lparn);
+                } else {
+                    ksteps(As, std::integral_constant<int, 4>{}, kg, kgroups);
+                    ok = false;
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    if (smem_add_relaxed(&done[ls], 1u) == uint32_t(nactive - 1)) {
-                        done[ls] = 0;
-                        if (step + NST < nsteps) issue(ls, step + NST);
-                    }
+                uint32_t last = 0;
+                if (lane == 0) last = (smem_add_relaxed(&done[ls], 1u) == uint32_t(nactive - 1)) ? 1u : 0u;
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    if (lane == 0) done[ls] = 0;
+                    if (step + NST < nsteps) issue(ls, step + NST);
                 }
                 ls = lsn;
                 lpar = lparn;
@@ -202,17 +230,68 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             par = np;
         }
         if (active) {
-            double* out = a.partial + (size_t(split) * a.npairs + pair) * (TB * TB);
+            double* out = a.partial + ((size_t(split) * a.njobs + jid) * NWARPS + warp) * TILE_DOUBLES;
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const int row = wr * 32 + mt * 8 + g;
-                        const int col = wc * 32 + nt * 8 + 2 * t + j;
-                        out[col * TB + row] = acc[mt][nt][j];
+                        const int row = mt * 8 + g;
+                        const int col = nt * 8 + 2 * t + j;
+                        out[col * CB + row] = acc[mt][nt][j];
                     }
+        }
+    }
+}
+
+// add the partial tiles in a fixed order and scatter into packed = [G (K x K) | C (K x T) | zz].
+// One block per (job, tile, 64-element slice); its four thread groups each add every fourth (row split, k-group)
+// partial in order and the four sums are combined as (s0 + s1) + (s2 + s3): the same order on every run.
+constexpr int RED_ELEMS = 64, RED_GROUPS = 4;
+__global__ void __launch_bounds__(RED_ELEMS * RED_GROUPS)
+gram_tma_reduce_kernel(const GramTmaArgs a, const double* __restrict__ zzpart, int nzz, double* __restrict__ packed) {
+    constexpr int SLICES = TILE_DOUBLES / RED_ELEMS;
+    const int slice = blockIdx.x % SLICES;
+    const int tile = (blockIdx.x / SLICES) % NWARPS;
+    const int jid = blockIdx.x / (SLICES * NWARPS);
+    const GramJob* const job = a.jobs + jid;
+    const int ntiles = job->ntiles, kgroups = job->kgroups;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nzz; ++i) s += zzpart[i];
+        packed[size_t(a.K) * a.K + size_t(a.K) * a.T] = s;
+    }
+    if (tile >= ntiles) return;
+    const int ba = job->slot_block[job->slot_a[tile]], bb = job->slot_block[job->slot_b[tile]];
+    const bool bz = bb >= a.kb;
+    const int e = slice * RED_ELEMS + (threadIdx.x % RED_ELEMS), grp = threadIdx.x / RED_ELEMS;
+    const int row = e % CB, col = e / CB;
+    const int ga = ba * CB + row;
+    const int gb = (bz ? bb - a.kb : bb) * CB + col;
+    const bool wanted = ga < a.K && gb < (bz ? a.T : a.K) && !(!bz && ba == bb && row > col);  // lower triangle of a
+                                                                                               // diagonal block is mirrored
+    __shared__ double sh[RED_GROUPS][RED_ELEMS];
+    double s = 0.0;
+    if (wanted) {
+        const int nparts = a.nsplit * kgroups;
+        for (int p = grp; p < nparts; p += RED_GROUPS) {
+            const int sp = p / kgroups, k = p % kgroups;
+            s += a.partial[((size_t(sp) * a.njobs + jid) * NWARPS + tile + k * ntiles) * TILE_DOUBLES + e];
+        }
+    }
+    sh[grp][threadIdx.x % RED_ELEMS] = s;
+    __syncthreads();
+    if (grp == 0 && wanted) {
+        const int i = threadIdx.x;
+        s = (sh[0][i] + sh[1][i]) + (sh[2][i] + sh[3][i]);
+        double* G = packed;
+        double* C = packed + size_t(a.K) * a.K;
+        if (bz) {
+            C[ga + size_t(gb) * a.K] = s;
+        } else {
+            G[ga + size_t(gb) * a.K] = s;
+            G[gb + size_t(ga) * a.K] = s;
         }
     }
 }
@@ -233,7 +312,7 @@ CUtensorMap make_map(const double* ptr, int64_t rows, int cols, int64_t ld) {
     CUtensorMap tm;
     cuuint64_t gdim[2] = {cuuint64_t(rows), cuuint64_t(cols)};
     cuuint64_t gstr[1] = {cuuint64_t(ld) * 8};
-    cuuint32_t box[2] = {KR, TB};
+    cuuint32_t box[2] = {KR, CB};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -242,7 +321,87 @@ CUtensorMap make_map(const double* ptr, int64_t rows, int cols, int64_t ld) {
     return tm;
 }
 
+// ---- host: pack the block pairs into jobs -------------------------------------------------------------------
+struct Piece {
+    std::vector<std::pair<int, int>> tiles;  // (block a, block b) in the combined F|Z block space
+    std::vector<int> blocks;                 // distinct blocks touched, ascending
+};
+
+int union_size(const std::vector<int>& x, const std::vector<int>& y) {
+    std::vector<int> u;
+    std::set_union(x.begin(), x.end(), y.begin(), y.end(), std::back_inserter(u));
+    return int(u.size());
+}
+
 }  // namespace
+
+std::vector<GramJobHost> gram_pack_jobs(int K, int T) {
+    const int kb = (K + CB - 1) / CB, zb = (T + CB - 1) / CB;
+    const int ng = (kb + 3) / 4, nzg = (zb + 3) / 4;
+    auto group = [](int gidx, int nblocks, int base) {
+        std::vector<int> b;
+        for (int i = 4 * gidx; i < std::min(nblocks, 4 * gidx + 4); ++i) b.push_back(base + i);
+        return b;
+    };
+    std::vector<Piece> pieces;
+    for (int ga = 0; ga < ng; ++ga) {
+        const std::vector<int> A = group(ga, kb, 0);
+        Piece d;  // diagonal macro tile: upper triangle only
+        for (size_t i = 0; i < A.size(); ++i)
+            for (size_t j = i; j < A.size(); ++j) d.tiles.push_back({A[i], A[j]});
+        d.blocks = A;
+        pieces.push_back(d);
+        for (int gb = ga + 1; gb < ng; ++gb) {
+            const std::vector<int> B = group(gb, kb, 0);
+            Piece o;
+            for (int x : A)
+                for (int y : B) o.tiles.push_back({x, y});
+            o.blocks = A;
+            o.blocks.insert(o.blocks.end(), B.begin(), B.end());
+            pieces.push_back(o);
+        }
+        for (int gz = 0; gz < nzg; ++gz) {
+            const std::vector<int> Z = group(gz, zb, kb);
+            Piece o;
+            for (int y : Z)
+                for (int x : A) o.tiles.push_back({x, y});
+            o.blocks = A;
+            o.blocks.insert(o.blocks.end(), Z.begin(), Z.end());
+            pieces.push_back(o);
+        }
+    }
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.tiles.size() > y.tiles.size(); });
+    // first-fit-decreasing merge, preferring the job that shares the most blocks
+    std::vector<Piece> jobs;
+    for (const Piece& p : pieces) {
+        int best = -1, best_new = 1 << 30;
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            if (jobs[j].tiles.size() + p.tiles.size() > size_t(NWARPS)) continue;
+            const int u = union_size(jobs[j].blocks, p.blocks);
+            if (u > MAXSLOTS) continue;
+            const int added = u - int(jobs[j].blocks.size());
+            if (added < best_new) { best_new = added; best = int(j); }
+        }
+        if (best < 0) {
+            jobs.push_back(p);
+        } else {
+            Piece& q = jobs[best];
+            q.tiles.insert(q.tiles.end(), p.tiles.begin(), p.tiles.end());
+            std::vector<int> u;
+            std::set_union(q.blocks.begin(), q.blocks.end(), p.blocks.begin(), p.blocks.end(), std::back_inserter(u));
+            q.blocks = u;
+        }
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const Piece& x, const Piece& y) { return x.tiles.size() > y.tiles.size(); });
+    std::vector<GramJobHost> out;
+    for (const Piece& p : jobs) {
+        GramJobHost h;
+        h.blocks = p.blocks;
+        h.tiles = p.tiles;
+        out.push_back(h);
+    }
+    return out;
+}
 
 bool gram_tma_usable(const double* dF, int64_t ldf, const double* dZ, int T, int64_t ldz, int64_t n) {
     if (reinterpret_cast<uintptr_t>(dF) % 16 || ldf % 2) return false;
@@ -252,39 +411,95 @@ bool gram_tma_usable(const double* dF, int64_t ldf, const double* dZ, int T, int
 }
 
 void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const double* dZ, int T, int64_t ldz,
-                        const double* dw, GramWorkspace& ws, int sms, GramLayout& lay, cudaStream_t st) {
+                        const double* dw, double* dpacked, GramWorkspace& ws, int sms, int nzz, cudaStream_t st) {
     GramTmaArgs a;
     a.K = K; a.T = T; a.n = n; a.w = dw;
-    a.ntf = (K + TB - 1) / TB;
-    a.ntz = (T + TB - 1) / TB;
-    a.npairs = a.ntf * (a.ntf + 1) / 2 + a.ntf * a.ntz;
-    // about six items per CTA for dynamic balance, at least 2048 rows per item
+    a.kb = (K + CB - 1) / CB;
+    // job table: cached per shape
+    if (ws.jobs_K != K || ws.jobs_T != T) {
+        const std::vector<GramJobHost> hj = gram_pack_jobs(K, T);
+        std::vector<GramJob> dj(hj.size());
+        for (size_t j = 0; j < hj.size(); ++j) {
+            GramJob& d = dj[j];
+            const GramJobHost& h = hj[j];
+            d = GramJob{};
+            d.nslots = int(h.blocks.size());
+            d.ntiles = int(h.tiles.size());
+            d.kgroups = d.ntiles <= 4 ? 4 : (d.ntiles <= 8 ? 2 : 1);
+            for (int i = 0; i < d.nslots; ++i) d.slot_block[i] = h.blocks[i];
+            // warp i runs on SM sub-partition i % 4: hand the tiles out heaviest first (cost = valid 8-column
+            // groups of block b) to the sub-partition with the least work that still has a free warp
+            std::vector<int> cost(d.ntiles), order(d.ntiles), warp_of(d.ntiles);
+            for (int i = 0; i < d.ntiles; ++i) {
+                const int bb = h.tiles[i].second;
+                const int valid = std::min(CB, bb < a.kb ? K - bb * CB : T - (bb - a.kb) * CB);
+                cost[i] = (valid + 7) / 8;
+                order[i] = i;
+            }
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+            int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            for (int i : order) {
+                int best = -1;
+                for (int sp = 0; sp < 4; ++sp) {
+                    if (sp + 4 * used[sp] >= d.ntiles) continue;  // no warp left on this sub-partition
+                    if (best < 0 || load[sp] < load[best]) best = sp;
+                }
+                warp_of[i] = best + 4 * used[best];
+                ++used[best];
+                load[best] += cost[i];
+            }
+            for (int i = 0; i < d.ntiles; ++i) {
+                const int wv = warp_of[i];
+                d.slot_a[wv] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].first) - h.blocks.begin());
+                d.slot_b[wv] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].second) - h.blocks.begin());
+                d.ntn[wv] = (unsigned char)cost[i];
+            }
+        }
+        const size_t bytes = sizeof(GramJob) * dj.size() + sizeof(unsigned);
+        ws.pair_order.alloc((bytes + sizeof(int) - 1) / sizeof(int));
+        FRK_CUDA(cudaMemcpyAsync(ws.pair_order.p, dj.data(), sizeof(GramJob) * dj.size(), cudaMemcpyHostToDevice, st));
+        FRK_CUDA(cudaStreamSynchronize(st));  // `dj` is a host temporary; only on a shape change
+        ws.jobs_K = K;
+        ws.jobs_T = T;
+        ws.njobs = int(dj.size());
+        int64_t units = 0;
+        for (const GramJob& d : dj) units += d.ntiles;
+        ws.job_tiles = int(units);
+    }
+    a.njobs = ws.njobs;
+    a.jobs = reinterpret_cast<const GramJob*>(ws.pair_order.p);
+    a.counter = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(ws.pair_order.p) + sizeof(GramJob) * a.njobs);
+    FRK_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st));
+    // Row splits.  Items are handed out dynamically, split-major; the tail of the launch costs up to one item of
+    // idle time per CTA, so the first 70% of the rows are cut into about four large items per CTA and the rest into
+    // about six items per CTA a quarter of that size (measured: 63.3 -> 59 ms at n = 5e6, K = 500, T = 100 against
+    // six equal items per CTA).  A single job makes all items equal: one per CTA.  At least 2048 rows per item.
+    static const int items_env = [] {
+        const char* e = std::getenv("FRK_GRAM_ITEMS");
+        return e ? std::atoi(e) : 0;
+    }();
+    auto round_rows = [](int64_t r) { return std::max<int64_t>(KR, (r + KR - 1) / KR * KR); };
     const int64_t max_split = std::max<int64_t>(1, n / 2048);
-    a.nsplit = int(std::max<int64_t>(1, std::min<int64_t>(max_split, (int64_t(sms) * 6 + a.npairs - 1) / a.npairs)));
-    a.rows_per_split = ((n + a.nsplit - 1) / a.nsplit + KR - 1) / KR * KR;
-    a.nitems = a.nsplit * a.npairs;
-    const size_t need = size_t(a.nitems) * TB * TB;
+    if (a.njobs == 1 || items_env > 0 || max_split < 16) {
+        const int per_cta = (a.njobs == 1) ? 1 : (items_env > 0 ? items_env : 6);
+        a.nsplit = int(std::max<int64_t>(1, std::min<int64_t>(max_split, (int64_t(sms) * per_cta + a.njobs - 1) / a.njobs)));
+        a.nsplit_big = a.nsplit;
+        a.rows_big = a.rows_small = round_rows((n + a.nsplit - 1) / a.nsplit);
+    } else {
+        const int64_t want_big = std::max<int64_t>(1, (int64_t(sms) * 4 + a.njobs - 1) / a.njobs);
+        const int64_t want_small = std::max<int64_t>(1, (int64_t(sms) * 6 + a.njobs - 1) / a.njobs);
+        const int64_t n_big = n / 10 * 7;
+        a.nsplit_big = int(std::min<int64_t>(want_big, std::max<int64_t>(1, n_big / 2048)));
+        a.rows_big = round_rows((n_big + a.nsplit_big - 1) / a.nsplit_big);
+        const int64_t n_small = std::max<int64_t>(0, n - int64_t(a.nsplit_big) * a.rows_big);
+        const int nsmall = int(std::min<int64_t>(want_small, std::max<int64_t>(1, n_small / 2048)));
+        a.rows_small = round_rows((n_small + nsmall - 1) / nsmall);
+        a.nsplit = a.nsplit_big + (n_small > 0 ? int((n_small + a.rows_small - 1) / a.rows_small) : 0);
+    }
+    a.nitems = a.nsplit * a.njobs;
+    const size_t need = size_t(a.nitems) * NWARPS * TILE_DOUBLES;
     if (ws.partial.n < need) ws.partial.alloc(need);
     a.partial = ws.partial.p;
-    // pair order: off-diagonal F x F, then F x Z, then the (cheaper) diagonal pairs; cached per tile shape
-    if (ws.order_ntf != a.ntf || ws.order_ntz != a.ntz) {
-        std::vector<int> order, diag_ids;
-        const int nff = a.ntf * (a.ntf + 1) / 2;
-        int id = 0;
-        for (int ta = 0; ta < a.ntf; ++ta)
-            for (int tb = ta; tb < a.ntf; ++tb, ++id) (ta == tb ? diag_ids : order).push_back(id);
-        for (id = nff; id < a.npairs; ++id) order.push_back(id);
-        order.insert(order.end(), diag_ids.begin(), diag_ids.end());
-        ws.pair_order.alloc(order.size() + 1);
-        FRK_CUDA(cudaMemcpyAsync(ws.pair_order.p, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, st));
-        FRK_CUDA(cudaStreamSynchronize(st));  // `order` is a host temporary; only on a shape change
-        ws.order_ntf = a.ntf;
-        ws.order_ntz = a.ntz;
-    }
-    unsigned* counter = reinterpret_cast<unsigned*>(ws.pair_order.p + a.npairs);
-    FRK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-    a.pair_order = ws.pair_order.p;
-    a.counter = counter;
 
     const CUtensorMap tmF = make_map(dF, n, K, ldf);
     const CUtensorMap tmZ = (T > 0) ? make_map(dZ, n, T, ldz) : tmF;
@@ -298,7 +513,11 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     if (dw) gram_tma_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tmF, tmZ, a);
     else gram_tma_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tmF, tmZ, a);
     FRK_CUDA(cudaGetLastError());
-    lay.ntf = a.ntf; lay.ntz = a.ntz; lay.npairs = a.npairs; lay.nsplit = a.nsplit;
+    gram_tma_reduce_kernel<<<a.njobs * NWARPS * (TILE_DOUBLES / RED_ELEMS), RED_ELEMS * RED_GROUPS, 0, st>>>(a, ws.zzpart.p, nzz,
+                                                                                                          dpacked);
+    FRK_CUDA(cudaGetLastError());
+    ws.last_nsplit = a.nsplit;
+    ws.last_npairs = a.njobs;
 }
 
 }  // namespace frk

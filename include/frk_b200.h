@@ -116,6 +116,12 @@ int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, i
                        double* G, double* C, double* zz);
 /* length of the packed device result [G (K*K) | C (K*T) | zz (1)] */
 int64_t frk_gram_packed_len(int32_t K, int32_t T);
+/* Host-only introspection of how the tensor-core Gram kernel cuts `t(Fk) %*% iDFk` / `t(Fk) %*% Data`
+ * (R/helper.R:20, R/autoFRK.R:433-435) into work: the 32-column block pairs (a <= b over F's blocks, then F x Z
+ * with Z's blocks numbered after F's) and the job each pair is packed into.  Writes up to `cap` triples
+ * (job, block_a, block_b) to `triples` (may be NULL) and returns the number of pairs; *njobs receives the job
+ * count.  No device work. */
+int64_t frk_gram_job_plan(int32_t K, int32_t T, int32_t* njobs, int32_t* triples, int64_t cap);
 /* device pointers: F n x K (ld ldf), Z n x T (ld ldz) -> d_packed; asynchronous on `stream`.
  * Multi-GPU: every rank calls this on its row shard, then one allreduce(sum) of d_packed. */
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,

@@ -61,3 +61,29 @@ def test_header_is_plain_c_and_shim_type_checks():
                         str(ROOT / "r" / "frk_b200_shim.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "error" not in r.stderr
+
+
+def test_gram_job_plan_covers_every_block_pair_once():
+    """Host-side packing of the Gram work (no device): every 32-column block pair (a <= b) of F'F and every
+    F x Z pair appears in exactly one job; a job holds <= 16 pairs over <= 8 distinct blocks."""
+    import numpy as np
+    from autofrk_b200 import _lib
+
+    lib = _lib.lib
+    for K, T in [(49, 0), (64, 4), (100, 1), (200, 20), (256, 1), (446, 1), (500, 1), (500, 100), (1000, 100), (1500, 33)]:
+        njobs = ctypes.c_int32(0)
+        count = lib.frk_gram_job_plan(K, T, ctypes.byref(njobs), None, 0)
+        tri = np.zeros((count, 3), dtype=np.int32)
+        assert lib.frk_gram_job_plan(K, T, ctypes.byref(njobs), tri.ctypes.data, count) == count
+        kb, zb = -(-K // 32), -(-T // 32)
+        want = {(a, b) for a in range(kb) for b in range(a, kb)} | {(a, kb + z) for a in range(kb) for z in range(zb)}
+        got = [(int(a), int(b)) for _, a, b in tri]
+        assert len(got) == len(set(got)) and set(got) == want, (K, T)
+        assert tri[:, 0].max() == njobs.value - 1
+        for j in range(njobs.value):
+            sel = tri[tri[:, 0] == j]
+            assert 1 <= len(sel) <= 16, (K, T, j)
+            assert len(set(sel[:, 1]) | set(sel[:, 2])) <= 8, (K, T, j)
+        # never more work than the 128-column tiling it replaced (16 warp tiles per tile pair, 10 on the diagonal)
+        ntf, ntz = -(-K // 128), -(-T // 128)
+        assert count <= 10 * ntf + 16 * (ntf * (ntf - 1) // 2 + ntf * ntz)

@@ -18,7 +18,8 @@ def _data(n, K, T, seed, rank=5):
 
 
 @pytest.mark.parametrize("n,K,T", [(5000, 30, 3), (20011, 130, 5), (4096, 128, 128), (30000, 500, 100), (777, 257, 1),
-                                   (3000, 40, 0)])
+                                   (3000, 40, 0), (20011, 64, 4), (9999, 100, 1), (15000, 200, 20), (8000, 49, 33),
+                                   (6000, 446, 1), (5000, 97, 40), (4000, 65, 0), (2500, 1000, 7)])
 def test_gram_stats_matches_numpy(n, K, T):
     from autofrk_b200 import frk as G
 
@@ -223,6 +224,12 @@ def test_weighted_gram_and_cMLEsp_diagonal_D():
     Gk, Ck, _ = G.gram_stats(F, Z[:, :1], weights=mask)
     o = mask > 0
     assert relmax(Gk, F[o].T @ F[o]) < 1e-12 and relmax(Ck, F[o].T @ Z[o, :1]) < 1e-12
+    for n2, K2, T2 in ((7003, 75, 3), (12001, 205, 37)):   # tensor-core job kernel (k-split and 16-tile jobs), weighted
+        F2, Z2 = _data(n2, K2, T2, seed=K2)
+        w2 = rng.random(n2) + 0.25
+        G2, C2, zz2 = G.gram_stats(F2, Z2, weights=w2)
+        assert relmax(G2, F2.T @ (w2[:, None] * F2)) < 1e-12 and relmax(C2, F2.T @ (w2[:, None] * Z2)) < 1e-12
+        assert abs(zz2 - np.sum(w2[:, None] * Z2 * Z2)) / zz2 < 1e-13
     D = 1.0 / w
     ref = O.cMLEsp(F, Z, D, wSave=True)
     got = G.cMLEsp(F, Z, D, wSave=True)

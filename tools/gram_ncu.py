@@ -7,7 +7,10 @@ import torch
 sys.path.insert(0, ".")
 from autofrk_b200 import _lib
 
-for n, K, T in ((2_000_000, 500, 100), (5_000_000, 32, 4)):
+shapes = ((2_000_000, 500, 100), (5_000_000, 32, 4))
+if len(sys.argv) > 1:  # n,K,T n,K,T ...
+    shapes = tuple(tuple(int(v) for v in arg.split(",")) for arg in sys.argv[1:])
+for n, K, T in shapes:
     F = torch.randn((K, n), dtype=torch.float64, device="cuda").T
     Z = torch.randn((T, n), dtype=torch.float64, device="cuda").T
     packed = torch.empty(_lib.lib.frk_gram_packed_len(K, T), dtype=torch.float64, device="cuda")

@@ -34,5 +34,6 @@ def run(n, K, T, reps=3):
 
 if __name__ == "__main__":
     out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(5_000_000, 32, 4), run(1_000_000, 1000, 100),
-           run(5_000_000, 200, 20)]
+           run(5_000_000, 200, 20), run(5_000_000, 256, 1), run(5_000_000, 100, 1), run(5_000_000, 64, 4),
+           run(2_000_000, 446, 1)]
     json.dump(out, open("gpurun_out/gram_probe.json", "w"), indent=1)
