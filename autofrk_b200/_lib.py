@@ -64,6 +64,7 @@ _SIGNATURES = {
     "frk_getHalf": (_i32, [_vp, _i64, _i32, _vp]),
     "frk_cMLEimat_stats": (_i32, [_vp, _i64, _vp, _i64, C.c_double, _i32, _i32, _i64, C.c_double, _i32, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _vp]),
+    "frk_cMLEimat_sweep": (_i32, [_vp, _i64, _vp, _i64, C.c_double, _i32, _i64, C.c_double, _vp, _i32, _vp]),
     "frk_cMLE": (_i32, [_vp, _i64, _i32, _i32, C.c_double, _vp, _vp, C.c_double, C.c_double, _i32, _i32, _i32,
                         C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "frk_plan_predict_frk": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),

@@ -11,11 +11,6 @@ frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, 
 
 namespace {
 
-#define FRK_CUBLAS(expr)                                                                       \
-    do {                                                                                       \
-        cublasStatus_t _s = (expr);                                                            \
-        if (_s != CUBLAS_STATUS_SUCCESS) ::frk::fail(3, "cuBLAS error %d at %s:%d", int(_s), __FILE__, __LINE__); \
-    } while (0)
 
 __global__ void axpy_kernel(double* __restrict__ acc, const double* __restrict__ x, int64_t len, int first) {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -235,6 +230,29 @@ int32_t frk_cMLEimat_stats(const double* G, int64_t ldg, const double* C, int64_
             if (w) FRK_CUDA(cudaMemcpy(w, out.w.p, sizeof(double) * K * T, cudaMemcpyDeviceToHost));
             if (V) FRK_CUDA(cudaMemcpy(V, out.V.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
         }
+    });
+}
+
+int32_t frk_cMLEimat_sweep(const double* G, int64_t ldg, const double* C, int64_t ldc, double zz, int32_t T, int64_t n,
+                           double s, const int32_t* Ks, int32_t nK, double* negloglik) {
+    return guarded([&] {
+        require_device();
+        if (nK < 1) return;
+        if (!G || !C || !Ks || !negloglik) frk::fail(FRK_EINVAL, "G, C, Ks and negloglik are required");
+        if (T < 1) frk::fail(FRK_EINVAL, "T must be positive");
+        int Kmax = 0;
+        for (int i = 0; i < nK; ++i) {
+            if (Ks[i] < 1) frk::fail(FRK_EINVAL, "every K must be positive");
+            Kmax = std::max(Kmax, int(Ks[i]));
+        }
+        if (ldg < Kmax || ldc < Kmax) frk::fail(FRK_EINVAL, "leading dimensions must be >= max(Ks)");
+        frk::DevBuf<double> dG(size_t(Kmax) * Kmax), dC(size_t(Kmax) * T);
+        FRK_CUDA(cudaMemcpy2D(dG.p, sizeof(double) * Kmax, G, sizeof(double) * ldg, sizeof(double) * Kmax, size_t(Kmax),
+                              cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemcpy2D(dC.p, sizeof(double) * Kmax, C, sizeof(double) * ldc, sizeof(double) * Kmax, size_t(T),
+                              cudaMemcpyHostToDevice));
+        std::vector<int> ks(Ks, Ks + nK);
+        frk::negloglik_sweep_dev(dG.p, Kmax, dC.p, Kmax, zz, T, double(n), s, ks.data(), nK, negloglik);
     });
 }
 

@@ -17,11 +17,6 @@
 
 namespace frk {
 
-#define FRK_CUBLAS(expr)                                                                       \
-    do {                                                                                       \
-        cublasStatus_t _s = (expr);                                                            \
-        if (_s != CUBLAS_STATUS_SUCCESS) ::frk::fail(3, "cuBLAS error %d at %s:%d", int(_s), __FILE__, __LINE__); \
-    } while (0)
 
 namespace {
 
@@ -212,6 +207,104 @@ void cmle_imat_from_stats_dev(const double* dG, int64_t ldg, const double* dC, i
     cmle_core_dev(half.p, JSJ.p, dC, ldc, K, T, n, trS, s, 0.0, wsave, only_loglik, false, 0.0, out);
     if (!only_loglik) {
         out.half = std::move(half);
+    }
+}
+
+// The K candidates of selectBasis use the leading K columns of one basis, i.e. the leading principal blocks G_K, C_K.
+// With G = L L' (Cholesky), L_K is the leading block of L and W_K = L_K^-1 C_K the leading K rows of W = L^-1 C
+// (forward substitution never looks ahead), and L_K^-1 = Q_K G_K^(-1/2) for an orthogonal Q_K, so
+//   JSJ_K = G_K^(-1/2) C_K C_K' G_K^(-1/2) / T   (R/autoFRK.R:433-435)   and   W_K W_K' / T
+// are orthogonally similar: same eigenvalues d, hence the same v (sol.v) and the same likelihood (:441-447).  The
+// non-zero eigenvalues are those of the min(K, T)-sized Gram of W_K.  One potrf + one trsm replace 2 x length(Ks)
+// K x K eigen-decompositions.
+void negloglik_sweep_dev(const double* dG, int64_t ldg, const double* dC, int64_t ldc, double zz, int T, double n, double s,
+                         const int* Ks, int nK, double* negloglik) {
+    if (nK < 1) return;
+    if (T < 1) fail(1, "T must be positive");
+    int Kmax = 0;
+    for (int i = 0; i < nK; ++i) {
+        if (Ks[i] < 1) fail(1, "every K must be positive");
+        Kmax = std::max(Kmax, Ks[i]);
+    }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    LinalgHandles& lh = linalg_handles();
+    FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
+    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, nullptr));
+    const double one = 1.0, zero = 0.0;
+    const double trS = zz / T;                                       // R/autoFRK.R:431
+    DevBuf<double> L(size_t(Kmax) * Kmax), W(size_t(Kmax) * T);
+    dim3 grid, block;
+    launch2d(Kmax, Kmax, grid, block);
+    copy_block_kernel<<<grid, block>>>(dG, ldg, Kmax, Kmax, L.p, Kmax);
+    launch2d(Kmax, T, grid, block);
+    copy_block_kernel<<<grid, block>>>(dC, ldc, Kmax, T, W.p, Kmax);
+    FRK_CUDA(cudaGetLastError());
+    std::vector<double> gdiag(Kmax), ldiag(Kmax);
+    FRK_CUDA(cudaMemcpy2D(gdiag.data(), sizeof(double), L.p, sizeof(double) * (Kmax + 1), sizeof(double), size_t(Kmax),
+                          cudaMemcpyDeviceToHost));
+    int lwork = 0;
+    FRK_CUSOLVER(cusolverDnDpotrf_bufferSize(lh.solver, CUBLAS_FILL_MODE_LOWER, Kmax, L.p, Kmax, &lwork));
+    DevBuf<double> work(static_cast<size_t>(std::max(lwork, 1)));
+    DevBuf<int> dinfo(1);
+    FRK_CUSOLVER(cusolverDnDpotrf(lh.solver, CUBLAS_FILL_MODE_LOWER, Kmax, L.p, Kmax, work.p, lwork, dinfo.p));
+    int info = 0;
+    FRK_CUDA(cudaMemcpy(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (info != 0) {  // not positive definite: nothing of the factor is trusted
+        for (int i = 0; i < nK; ++i) negloglik[i] = nan;
+        return;
+    }
+    FRK_CUDA(cudaMemcpy2D(ldiag.data(), sizeof(double), L.p, sizeof(double) * (Kmax + 1), sizeof(double), size_t(Kmax),
+                          cudaMemcpyDeviceToHost));
+    // largest K whose leading block is safely positive definite: pivots^2 above 1e-10 of the largest diagonal so far
+    // (below that the reference's eigenvalue rule, R/helper.R:22-24, and a Cholesky factor may part ways)
+    int Ksafe = 0;
+    {
+        double gmax = 0.0;
+        for (int i = 0; i < Kmax; ++i) {
+            gmax = std::fmax(gmax, gdiag[i]);
+            if (!(ldiag[i] * ldiag[i] > 1e-10 * gmax)) break;
+            Ksafe = i + 1;
+        }
+    }
+    FRK_CUBLAS(cublasDtrsm(lh.blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, Kmax, T, &one,
+                           L.p, Kmax, W.p, Kmax));
+    std::vector<double> w1;
+    if (T == 1) {  // rank one: d = (|W_K|^2, 0, ..., 0)
+        w1.resize(Kmax);
+        FRK_CUDA(cudaMemcpy(w1.data(), W.p, sizeof(double) * Kmax, cudaMemcpyDeviceToHost));
+    }
+    const int mmax = std::min(Kmax, T);
+    DevBuf<double> S(size_t(mmax) * mmax), vals(static_cast<size_t>(mmax));
+    DevBuf<double> ework;
+    const double invT = 1.0 / T;
+    for (int i = 0; i < nK; ++i) {
+        const int K = Ks[i];
+        if (K > Ksafe) { negloglik[i] = nan; continue; }
+        const int m = std::min(K, T);
+        std::vector<double> d(K, 0.0);
+        if (T == 1) {
+            double acc = 0.0;
+            for (int j = 0; j < K; ++j) acc += w1[j] * w1[j];
+            d[0] = acc;
+        } else {
+            if (T <= K)
+                FRK_CUBLAS(cublasDsyrk(lh.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, m, K, &invT, W.p, Kmax, &zero, S.p, m));
+            else
+                FRK_CUBLAS(cublasDsyrk(lh.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, m, T, &invT, W.p, Kmax, &zero, S.p, m));
+            int lw = 0;
+            FRK_CUSOLVER(cusolverDnDsyevd_bufferSize(lh.solver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, m, S.p, m,
+                                                     vals.p, &lw));
+            if (ework.n < size_t(lw)) ework.alloc(static_cast<size_t>(lw));
+            FRK_CUSOLVER(cusolverDnDsyevd(lh.solver, CUSOLVER_EIG_MODE_NOVECTOR, CUBLAS_FILL_MODE_LOWER, m, S.p, m, vals.p,
+                                          ework.p, lw, dinfo.p));
+            std::vector<double> asc(m);
+            FRK_CUDA(cudaMemcpy(asc.data(), vals.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+            FRK_CUDA(cudaMemcpy(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+            if (info != 0) fail(4, "symmetric eigen decomposition did not converge (info=%d)", info);
+            for (int j = 0; j < m; ++j) d[j] = std::fmax(asc[m - 1 - j], 0.0);   // descending; :445
+        }
+        const double v = sol_v(d, s, trS, n);                        // :444
+        negloglik[i] = neg2llik(d, s, v, trS, n) * T;                // :447
     }
 }
 

@@ -28,4 +28,10 @@ void cmle_core_dev(const double* dhalf, double* dJSJ, const double* dC, int64_t 
 void cmle_imat_from_stats_dev(const double* dG, int64_t ldg, const double* dC, int64_t ldc, double zz, int K, int T,
                               double n, double s, bool wsave, bool only_loglik, CmleOut& out);
 
+// selectBasis' AIC sweep (R/autoFRK.R:305-317): negloglik of cMLEimat(Fk[, 1:K], Data, s, onlylogLike) for every K in
+// Ks from ONE Cholesky factor of the max-K Gram matrix.  Entries the factor cannot serve (G not safely positive
+// definite up to that K) are set to NaN -- the caller then takes the eigen path (cmle_imat_from_stats_dev) for them.
+void negloglik_sweep_dev(const double* dG, int64_t ldg, const double* dC, int64_t ldc, double zz, int T, double n, double s,
+                         const int* Ks, int nK, double* negloglik);
+
 }  // namespace frk

@@ -12,16 +12,6 @@ using frk_capi::require_device;
 
 namespace {
 
-#define FRK_CUBLAS(expr)                                                                       \
-    do {                                                                                       \
-        cublasStatus_t _s = (expr);                                                            \
-        if (_s != CUBLAS_STATUS_SUCCESS) ::frk::fail(3, "cuBLAS error %d at %s:%d", int(_s), __FILE__, __LINE__); \
-    } while (0)
-#define FRK_CUSOLVER(expr)                                                                     \
-    do {                                                                                       \
-        cusolverStatus_t _s = (expr);                                                          \
-        if (_s != CUSOLVER_STATUS_SUCCESS) ::frk::fail(3, "cuSOLVER error %d at %s:%d", int(_s), __FILE__, __LINE__); \
-    } while (0)
 
 __global__ void em_axpy_kernel(double* __restrict__ acc, const double* __restrict__ x, int64_t len, int first) {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;

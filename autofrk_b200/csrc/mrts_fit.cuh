@@ -6,6 +6,17 @@
 
 namespace frk {
 
+#define FRK_CUBLAS(expr)                                                                       \
+    do {                                                                                       \
+        cublasStatus_t _s = (expr);                                                            \
+        if (_s != CUBLAS_STATUS_SUCCESS) ::frk::fail(3, "cuBLAS error %d at %s:%d", int(_s), __FILE__, __LINE__); \
+    } while (0)
+#define FRK_CUSOLVER(expr)                                                                     \
+    do {                                                                                       \
+        cusolverStatus_t _s = (expr);                                                          \
+        if (_s != CUSOLVER_STATUS_SUCCESS) ::frk::fail(3, "cuSOLVER error %d at %s:%d", int(_s), __FILE__, __LINE__); \
+    } while (0)
+
 struct LinalgHandles {
     int device = -1;
     cublasHandle_t blas = nullptr;

@@ -95,6 +95,20 @@ def cmle_from_stats(G, Cm, zz, n, TT, s=0.0, wSave=False, onlylogLike=None, K=No
     return out
 
 
+def cmle_sweep_from_stats(G, Cm, zz, n, TT, Ks, s=0.0):
+    """negloglik of cMLEimat(Fk[, 1:K], Data, s)$negloglik for every K in Ks (the loop at R/autoFRK.R:305-317) from the
+    max-K statistics: one Cholesky factor of G serves all leading blocks (frk_cMLEimat_sweep); a K it cannot serve
+    (G not safely positive definite) goes through the eigen path of cmle_from_stats."""
+    G, Cm = fmat(G, "G"), fmat(Cm, "C")
+    ks = np.ascontiguousarray(np.asarray(Ks, dtype=np.int32))
+    out = np.empty(ks.size, dtype=np.float64)
+    check(lib.frk_cMLEimat_sweep(ptr(G), G.shape[0], ptr(Cm), Cm.shape[0], float(zz), int(TT), int(n), float(s),
+                                 ks.ctypes.data_as(C.c_void_p), int(ks.size), out.ctypes.data_as(C.c_void_p)))
+    for i in np.nonzero(np.isnan(out))[0]:
+        out[i] = cmle_from_stats(G, Cm, zz, n, TT, s=s, wSave=False, onlylogLike=True, K=int(ks[i]))["negloglik"]
+    return out
+
+
 def cMLEimat(Fk, Data, s, wSave=False, S=None, onlylogLike=None):
     """R/autoFRK.R:399-480."""
     if S is not None:
@@ -377,9 +391,7 @@ def selectBasis(Data, loc, D=None, maxit=50, avgtol=1e-6, maxK=None, Kseq=None, 
     if iD is not None:
         iD = iD[pick]
     G, Cm, zz = gram_stats(np.asfortranarray(Fk.X[pick]), Z, weights=iD)   # one pass; trS = zz/TT (:304)
-    AIC = np.full(K.size, np.inf)
-    for i, k in enumerate(K):                                   # :305-317
-        AIC[i] = cmle_from_stats(G, Cm, zz, N, TT, s=0.0, wSave=False, onlylogLike=True, K=int(k))["negloglik"]
+    AIC = cmle_sweep_from_stats(G, Cm, zz, N, TT, K, s=0.0)    # :305-317, all K from one Cholesky factor
     df = np.where(K <= TT, K * (K + 1) / 2 + 1, K * TT + 1 - TT * (TT - 1) / 2)   # :321
     AIC = AIC + 2 * df                                          # :322
     Kopt = int(K[np.argmin(AIC)])                               # :323

@@ -150,6 +150,15 @@ int32_t frk_cMLEimat_stats(const double* G, int64_t ldg, const double* C, int64_
                            int64_t n, double s, int32_t wsave, int32_t only_loglik, int32_t on_device, double* v,
                            double* negloglik, double* M, double* w, double* V);
 
+/* The K loop of selectBasis (R/autoFRK.R:305-317): negloglik[i] = cMLEimat(Fk[, 1:Ks[i]], Data, s, wSave = FALSE)$negloglik
+ * for every candidate basis size, from the max-K statistics G (>= max(Ks) square, ld ldg), C (ld ldc), zz (host
+ * pointers).  One Cholesky factor of G serves every leading block (the eigenvalues of JSJ_K are those of the
+ * min(K, T)-sized Gram of the leading K rows of L^-1 C), instead of two K x K eigen-decompositions per candidate.
+ * Candidates whose leading block of G is not safely positive definite get NaN: call frk_cMLEimat_stats for them
+ * (it follows getHalf's zero-eigenvalue rule, R/helper.R:22-24). */
+int32_t frk_cMLEimat_sweep(const double* G, int64_t ldg, const double* C, int64_t ldc, double zz, int32_t T, int64_t n,
+                           double s, const int32_t* Ks, int32_t nK, double* negloglik);
+
 /* cMLE (R/autoFRK.R:333-397): half, JSJ are K x K host matrices; Fk (n x K, host, may be NULL) is only needed
  * for L (n x nL, written when wsave != 0 and Fk, L are non-NULL; L must hold n x K doubles). */
 int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS, const double* half, const double* JSJ,

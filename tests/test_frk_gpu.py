@@ -76,6 +76,45 @@ def test_gram_dev_and_fused_predict_gram():
     assert relmax(fused.cpu().numpy(), packed.cpu().numpy()) < 1e-12
 
 
+@pytest.mark.parametrize("n,Kmax,T,s", [(6000, 60, 1, 0.0), (6000, 60, 7, 0.0), (3000, 40, 64, 0.0), (5000, 33, 5, 0.3)])
+def test_cMLEimat_sweep_matches_oracle_per_K(n, Kmax, T, s):
+    """the K loop of selectBasis (R/autoFRK.R:305-317) from one Cholesky factor: the same negloglik as the oracle's
+    literal cMLEimat(Fk[, 1:K], ...) and as the per-K eigen path, for every K, T < K and T >= K alike."""
+    import oracle as O
+    from autofrk_b200 import frk as G
+
+    F, Z = _data(n, Kmax, T, seed=Kmax + T)
+    Gm, Cm, zz = G.gram_stats(F, Z)
+    Ks = [1, 2, 3, 5, 8, 13, 21, Kmax - 1, Kmax]
+    got = G.cmle_sweep_from_stats(Gm, Cm, zz, n, T, Ks, s=s)
+    for k, nll in zip(Ks, got):
+        ref = O.cMLEimat(F[:, :k], Z, s, wSave=False)["negloglik"]
+        eig = G.cmle_from_stats(Gm, Cm, zz, n, T, s=s, onlylogLike=True, K=k)["negloglik"]
+        assert abs(nll - ref) <= TOL * abs(ref), (k, nll, ref)
+        assert abs(nll - eig) <= TOL * abs(eig), (k, nll, eig)
+
+
+def test_cMLEimat_sweep_falls_back_on_singular_gram():
+    """a rank-deficient basis (duplicated column): the Cholesky factor is refused from that K on (NaN from the C ABI)
+    and the wrapper takes the eigen path with getHalf's zero-eigenvalue rule (R/helper.R:22-24)."""
+    import ctypes as C
+    from autofrk_b200 import _lib, frk as G
+
+    n, T = 4000, 3
+    F, Z = _data(n, 12, T, seed=3)
+    F = np.asfortranarray(np.column_stack([F[:, :8], F[:, 2], F[:, 8:]]))     # column 8 duplicates column 2
+    Gm, Cm, zz = G.gram_stats(F, Z)
+    Ks = np.array([4, 8, 9, 13], dtype=np.int32)
+    raw = np.empty(Ks.size)
+    _lib.check(_lib.lib.frk_cMLEimat_sweep(_lib.ptr(Gm), 13, _lib.ptr(Cm), 13, zz, T, n, 0.0, Ks.ctypes.data_as(C.c_void_p),
+                                           Ks.size, raw.ctypes.data_as(C.c_void_p)))
+    assert np.isfinite(raw[:2]).all() and np.isnan(raw[2:]).all()
+    got = G.cmle_sweep_from_stats(Gm, Cm, zz, n, T, Ks)
+    for k, nll in zip(Ks, got):
+        eig = G.cmle_from_stats(Gm, Cm, zz, n, T, onlylogLike=True, K=int(k))["negloglik"]
+        assert abs(nll - eig) <= TOL * abs(eig)
+
+
 @pytest.mark.parametrize("n,K,T,s", [(4000, 12, 5, 0.0), (20000, 60, 20, 0.0), (3000, 40, 1, 0.0), (5000, 25, 8, 0.5)])
 def test_cMLEimat_matches_oracle(n, K, T, s):
     import oracle as O
