@@ -116,14 +116,18 @@ void half_from_gram_dev(const double* dG, int64_t ldg, int K, double* dhalf) {
 
 void cmle_core_dev(const double* dhalf, double* dJSJ /* K x K, lower triangle valid; destroyed */, const double* dC,
                    int64_t ldc, int K, int T, double n, double trS, double s, double ldet, bool wsave, bool only_loglik,
-                   bool has_vfixed, double vfixed, CmleOut& out) {
+                   bool has_vfixed, double vfixed, CmleOut& out, const std::vector<double>* eigen_asc) {
     LinalgHandles& lh = linalg_handles();
     FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
     const double one = 1.0, zero = 0.0;
-    DevBuf<double> dval(static_cast<size_t>(K));
-    sym_eigen_dev(dJSJ, K, dval.p);                                 // R/autoFRK.R:368 / :441  (P ascending in dJSJ)
     std::vector<double> asc(K), d(K);
-    FRK_CUDA(cudaMemcpy(asc.data(), dval.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+    if (eigen_asc) {                                                // dJSJ already holds P (ascending), see below
+        asc = *eigen_asc;
+    } else {
+        DevBuf<double> dval(static_cast<size_t>(K));
+        sym_eigen_dev(dJSJ, K, dval.p);                             // R/autoFRK.R:368 / :441  (P ascending in dJSJ)
+        FRK_CUDA(cudaMemcpy(asc.data(), dval.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+    }
     for (int i = 0; i < K; ++i) d[i] = asc[K - 1 - i];              // R's eigen(): descending
     const double v = has_vfixed ? vfixed : sol_v(d, s, trS, n);     // :371-375 / :444
     std::vector<double> dii(K);
@@ -203,8 +207,34 @@ void cmle_imat_from_stats_dev(const double* dG, int64_t ldg, const double* dC, i
     // ihF %*% Data = half %*% C                                       :433-435
     FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, T, K, &one, half.p, K, dC, int(ldc), &zero, t.p, K));
     const double invT = 1.0 / T;                                    // tcrossprod(.)/TT; lower triangle == (JSJ+JSJ')/2 :440
-    FRK_CUBLAS(cublasDsyrk(lh.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, K, T, &invT, t.p, K, &zero, JSJ.p, K));
-    cmle_core_dev(half.p, JSJ.p, dC, ldc, K, T, n, trS, s, 0.0, wsave, only_loglik, false, 0.0, out);
+    if (T < K) {
+        // JSJ = t t'/T has rank <= T: its non-zero eigenpairs come from the T x T matrix S = t't/T = U diag(lam) U'
+        // as P_j = t U_j / sqrt(T lam_j); the other K-T eigenvalues are exactly 0 and, with dhat = 0, their
+        // eigenvectors never enter M, w, V or L (:376-391, :451-474), so those columns are left zero.
+        DevBuf<double> S(size_t(T) * T), lam(static_cast<size_t>(T)), sc(static_cast<size_t>(T));
+        FRK_CUBLAS(cublasDsyrk(lh.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, T, K, &invT, t.p, K, &zero, S.p, T));
+        sym_eigen_dev(S.p, T, lam.p);                               // ascending
+        std::vector<double> lam_h(T), sc_h(T), asc(K, 0.0);
+        FRK_CUDA(cudaMemcpy(lam_h.data(), lam.p, sizeof(double) * T, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < T; ++j) {
+            const double l = std::fmax(lam_h[j], 0.0);
+            asc[K - T + j] = l;
+            sc_h[j] = (l > 0.0) ? 1.0 / std::sqrt(double(T) * l) : 0.0;
+        }
+        FRK_CUDA(cudaMemcpy(sc.p, sc_h.data(), sizeof(double) * T, cudaMemcpyHostToDevice));
+        FRK_CUDA(cudaMemset(JSJ.p, 0, sizeof(double) * size_t(K) * (K - T)));
+        double* Pnz = JSJ.p + size_t(K) * (K - T);
+        DevBuf<double> tu(size_t(K) * T);
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, T, T, &one, t.p, K, S.p, T, &zero, tu.p, K));
+        dim3 grid, block;
+        launch2d(K, T, grid, block);
+        scale_cols_kernel<<<grid, block>>>(tu.p, K, T, sc.p, Pnz);
+        FRK_CUDA(cudaGetLastError());
+        cmle_core_dev(half.p, JSJ.p, dC, ldc, K, T, n, trS, s, 0.0, wsave, only_loglik, false, 0.0, out, &asc);
+    } else {
+        FRK_CUBLAS(cublasDsyrk(lh.blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, K, T, &invT, t.p, K, &zero, JSJ.p, K));
+        cmle_core_dev(half.p, JSJ.p, dC, ldc, K, T, n, trS, s, 0.0, wsave, only_loglik, false, 0.0, out);
+    }
     if (!only_loglik) {
         out.half = std::move(half);
     }

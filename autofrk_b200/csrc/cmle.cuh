@@ -20,9 +20,11 @@ double neg2llik(const std::vector<double>& d, double s, double v, double trS, do
 // half = G^(-1/2) with zero eigenvalues -> 0 (getHalf, R/helper.R:19-26); dG is K x K with leading dimension ldg
 void half_from_gram_dev(const double* dG, int64_t ldg, int K, double* dhalf);
 
-// cMLE (R/autoFRK.R:333-397) given half and JSJ on the device (JSJ is destroyed)
+// cMLE (R/autoFRK.R:333-397) given half and JSJ on the device (JSJ is destroyed).  eigen_asc != nullptr: dJSJ already
+// holds JSJ's eigenvectors (columns in ascending eigenvalue order) and *eigen_asc the K eigenvalues.
 void cmle_core_dev(const double* dhalf, double* dJSJ, const double* dC, int64_t ldc, int K, int T, double n, double trS,
-                   double s, double ldet, bool wsave, bool only_loglik, bool has_vfixed, double vfixed, CmleOut& out);
+                   double s, double ldet, bool wsave, bool only_loglik, bool has_vfixed, double vfixed, CmleOut& out,
+                   const std::vector<double>* eigen_asc = nullptr);
 
 // cMLEimat (R/autoFRK.R:399-480) from the sufficient statistics G (ld ldg), C (ld ldc), zz
 void cmle_imat_from_stats_dev(const double* dG, int64_t ldg, const double* dC, int64_t ldc, double zz, int K, int T,

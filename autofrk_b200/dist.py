@@ -25,6 +25,36 @@ def world():
     return 1, 0
 
 
+def bind_to_gpu_numa(device_index: int) -> int:
+    """Pin this process to the CPUs NVML reports as local to the GPU, before any pinned host buffer is allocated,
+    so that the host side of the H2D / D2H copies (predict.mrts returns an n2 x K host matrix) stays on the GPU's
+    own socket.  Returns the number of CPUs bound to, or 0 when nothing was changed (no NVML, or the local CPUs
+    are outside this process's cpuset)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            tok = visible.split(",")[device_index].strip()
+            handle = pynvml.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(ncpu, 1024) + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def shard_rows(n: int, world_size: int, rank: int):
     """Contiguous row block of `rank`; block starts are even so that every shard of a column-major
     matrix with even leading dimension stays 16-byte aligned (the Gram kernel's cp.async fast path)."""

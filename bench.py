@@ -202,6 +202,8 @@ def main_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (autofrk_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
+    from autofrk_b200.dist import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local)     # host buffers of the e2e leg on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOAD
@@ -308,7 +310,7 @@ def main_gpu(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n2e * d * 8),
                     "d2h_bytes_per_step": int(n2e * K * 8),
                     "sample": f"{n2e} rows/GPU per step through frk_plan_predict (host buffers, pinned)",
-                    "matches_device_path": same},
+                    "matches_device_path": same, "cpus_bound_to_gpu_socket": numa_cpus},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
         }

@@ -115,7 +115,8 @@ def test_cMLEimat_sweep_falls_back_on_singular_gram():
         assert abs(nll - eig) <= TOL * abs(eig)
 
 
-@pytest.mark.parametrize("n,K,T,s", [(4000, 12, 5, 0.0), (20000, 60, 20, 0.0), (3000, 40, 1, 0.0), (5000, 25, 8, 0.5)])
+@pytest.mark.parametrize("n,K,T,s", [(4000, 12, 5, 0.0), (20000, 60, 20, 0.0), (3000, 40, 1, 0.0), (5000, 25, 8, 0.5),
+                                     (3000, 8, 12, 0.0), (3000, 10, 10, 0.2)])
 def test_cMLEimat_matches_oracle(n, K, T, s):
     import oracle as O
     from autofrk_b200 import frk as G
