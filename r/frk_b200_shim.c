@@ -146,6 +146,19 @@ SEXP _autoFRK_cMLEimat_stats(SEXP G, SEXP C, SEXP zz, SEXP n_, SEXP s_, SEXP wSa
     return out;
 }
 
+/* selectBasis' K loop (R/autoFRK.R:305-317): negloglik for every K in `Ks` (integer vector) from the max-K statistics */
+SEXP _autoFRK_cMLEimat_sweep(SEXP G, SEXP C, SEXP zz, SEXP TT_, SEXP n_, SEXP s_, SEXP Ks) {
+    need_real_matrix(G, "G");
+    need_real_matrix(C, "C");
+    if (TYPEOF(Ks) != INTSXP) Rf_error("Ks must be an integer vector");
+    int nK = (int)XLENGTH(Ks);
+    SEXP nll = PROTECT(Rf_allocVector(REALSXP, nK));
+    check(frk_cMLEimat_sweep(REAL(G), Rf_nrows(G), REAL(C), Rf_nrows(C), Rf_asReal(zz), Rf_asInteger(TT_),
+                             (int64_t)Rf_asReal(n_), Rf_asReal(s_), INTEGER(Ks), nK, REAL(nll)));
+    UNPROTECT(1);
+    return nll;   /* NaN entries: the caller uses _autoFRK_cMLEimat_stats on the leading blocks for that K */
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_getASCeigens", (DL_FUNC)&_autoFRK_getASCeigens, 1},
     {"_autoFRK_mrtsrcpp", (DL_FUNC)&_autoFRK_mrtsrcpp, 3},
@@ -154,6 +167,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_gram_stats", (DL_FUNC)&_autoFRK_gram_stats, 2},
     {"_autoFRK_getHalf_stats", (DL_FUNC)&_autoFRK_getHalf_stats, 1},
     {"_autoFRK_cMLEimat_stats", (DL_FUNC)&_autoFRK_cMLEimat_stats, 6},
+    {"_autoFRK_cMLEimat_sweep", (DL_FUNC)&_autoFRK_cMLEimat_sweep, 7},
     {NULL, NULL, 0}};
 
 void R_init_autoFRK(DllInfo *dll) {
