@@ -6,6 +6,7 @@
 typedef struct SEXPREC *SEXP;
 typedef ptrdiff_t R_xlen_t;
 typedef enum { FALSE = 0, TRUE } Rboolean;
+#define INTSXP 13
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
