@@ -17,6 +17,7 @@ R_xlen_t XLENGTH(SEXP);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 double *REAL(SEXP);
+int *INTEGER(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
 SEXP Rf_mkChar(const char *);
