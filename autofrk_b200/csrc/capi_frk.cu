@@ -27,6 +27,25 @@ __global__ void rowdot_sqrt_kernel(const double* __restrict__ FV, const double* 
     se[i] = sqrt(fmax(0.0, s));
 }
 
+// se[i] = sqrt(max(0, sum_j sgn[j] * Y[i,j]^2)): rowSums((basis V) * basis) with V = R diag(sgn) R', Y = basis R
+__global__ void signed_rownorm_kernel(const double* __restrict__ Y, int64_t rows, int64_t ld, int r,
+                                      const double* __restrict__ sgn, double* __restrict__ se) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= rows) return;
+    double s = 0.0;
+    for (int j = 0; j < r; ++j) {
+        const double y = Y[i + int64_t(j) * ld];
+        s = fma(sgn[j] * y, y, s);
+    }
+    se[i] = sqrt(fmax(0.0, s));
+}
+
+__global__ void scale_cols_inplace_kernel(double* __restrict__ A, int n, int cols, const double* __restrict__ f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < n && j < cols) A[i + int64_t(j) * n] *= f[j];
+}
+
 // One-shot all-reduce over NVLink peer memory: every rank reads every rank's packed statistics straight from the
 // peers' HBM (P2P loads through NVSwitch) and adds them in rank order, so all ranks obtain bitwise-identical sums.
 struct PeerPtrs {
@@ -301,40 +320,78 @@ int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, con
         frk::MrtsPlan* mp = plan->mp;
         const int K = mp->k, d = mp->d;
         if (T < 1 || !w || !yhat) frk::fail(FRK_EINVAL, "w (K x T) and yhat (n2 x T) are required");
-        frk::LinalgHandles& lh = frk::linalg_handles();
         cudaStream_t st = nullptr;
-        FRK_CUBLAS(cublasSetStream(lh.blas, st));
-        int64_t rc = std::min<int64_t>(n2, default_chunk_rows(mp, K) / 2);
-        frk::DevBuf<double> dx(size_t(n2) * d), dw(size_t(K) * T), dV, dy(size_t(rc) * T), dFV, dse;
-        if (plan->fchunk.n < size_t(rc) * K) plan->fchunk.alloc(size_t(rc) * K);
-        FRK_CUDA(cudaMemcpy(dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice));
-        FRK_CUDA(cudaMemcpy(dw.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice));
         const bool want_se = (V != nullptr && se != nullptr);
+        // Coefficient matrix B = [w | R] with V = R diag(sgn) R' (eigen-decomposition of V, |lambda| below
+        // 1e-15 max|lambda| dropped: that is below the rounding of the reference's own FP64 evaluation).  Then
+        //   yhat = basis %*% w                                   R/autoFRK.R:1216
+        //   se^2 = rowSums((basis %*% V) * basis) = sum_j sgn_j (basis %*% R)[, j]^2   R/autoFRK.R:1220
+        // and basis %*% B comes straight out of K1 through a derived plan (W' = W B_rest): q = T + rank(V) columns
+        // of tensor work instead of K columns plus an n2 x K x K product, and no n2 x K basis anywhere.
+        // V from cMLEimat has rank <= min(K, T).
+        std::vector<double> sgn;
+        frk::DevBuf<double> dB;
+        int r = 0;
         if (want_se) {
-            dV.alloc(size_t(K) * K);
-            dFV.alloc(size_t(rc) * K);
-            dse.alloc(static_cast<size_t>(rc));
+            frk::DevBuf<double> dV(size_t(K) * K), lam(static_cast<size_t>(K));
             FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+            frk::sym_eigen_dev(dV.p, K, lam.p);                     // ascending; lower triangle of V is read
+            std::vector<double> lam_h(K);
+            FRK_CUDA(cudaMemcpy(lam_h.data(), lam.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+            double amax = 0.0;
+            for (double l : lam_h) amax = std::fmax(amax, std::fabs(l));
+            std::vector<int> keep;
+            for (int i = K - 1; i >= 0; --i)
+                if (std::fabs(lam_h[i]) > 1e-15 * amax) keep.push_back(i);
+            r = int(keep.size());
+            dB.alloc(size_t(K) * (T + std::max(r, 1)));
+            std::vector<double> scale(std::max(r, 1));
+            for (int j = 0; j < r; ++j) {
+                scale[j] = std::sqrt(std::fabs(lam_h[keep[j]]));
+                sgn.push_back(lam_h[keep[j]] < 0.0 ? -1.0 : 1.0);
+                FRK_CUDA(cudaMemcpyAsync(dB.p + size_t(K) * (T + j), dV.p + size_t(K) * keep[j], sizeof(double) * K,
+                                         cudaMemcpyDeviceToDevice, st));
+            }
+            if (r > 0) {
+                frk::DevBuf<double> dscale(static_cast<size_t>(r));
+                FRK_CUDA(cudaMemcpyAsync(dscale.p, scale.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
+                dim3 grid(unsigned((K + 127) / 128), unsigned(r));
+                scale_cols_inplace_kernel<<<grid, 128, 0, st>>>(dB.p + size_t(K) * T, K, r, dscale.p);
+                FRK_CUDA(cudaGetLastError());
+                FRK_CUDA(cudaStreamSynchronize(st));
+            }
+        } else {
+            dB.alloc(size_t(K) * T);
         }
-        const double one = 1.0, zero = 0.0;
+        FRK_CUDA(cudaMemcpyAsync(dB.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice, st));
+        const int q = T + r;
+        struct PlanGuard {
+            frk::MrtsPlan* p;
+            ~PlanGuard() { frk::plan_destroy(p); }
+        } derived{frk::plan_derive_dev(mp, dB.p, q, st)};
+
+        int64_t rc = std::min<int64_t>(n2, default_chunk_rows(derived.p, q));
+        frk::DevBuf<double> dx(size_t(n2) * d), dy(size_t(rc) * q), dse, dsgn;
+        FRK_CUDA(cudaMemcpyAsync(dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, st));
+        if (want_se) {
+            dse.alloc(static_cast<size_t>(rc));
+            dsgn.alloc(static_cast<size_t>(std::max(r, 1)));
+            if (r > 0) FRK_CUDA(cudaMemcpyAsync(dsgn.p, sgn.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
+        }
         for (int64_t r0 = 0; r0 < n2; r0 += rc) {
             const int64_t rows = std::min(rc, n2 - r0);
-            frk::plan_predict_basis_dev(mp, dx.p + r0, rows, n2, plan->fchunk.p, rc, st);
-            // yhat = basis %*% w                                          R/autoFRK.R:1216
-            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), T, K, &one, plan->fchunk.p, int(rc), dw.p, K,
-                                   &zero, dy.p, int(rc)));
+            frk::plan_predict_x1_dev(derived.p, dx.p + r0, rows, n2, dy.p, rc, st);
             FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n2, dy.p, sizeof(double) * rc, sizeof(double) * rows,
                                        size_t(T), cudaMemcpyDeviceToHost, st));
             if (want_se) {
-                // se = sqrt(pmax(0, rowSums((basis %*% V) * basis)))       R/autoFRK.R:1220
-                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), K, K, &one, plan->fchunk.p, int(rc), dV.p,
-                                       K, &zero, dFV.p, int(rc)));
-                rowdot_sqrt_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dFV.p, plan->fchunk.p, rows, rc, K, dse.p);
+                signed_rownorm_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dy.p + size_t(rc) * T, rows, rc, r, dsgn.p,
+                                                                                   dse.p);
                 FRK_CUDA(cudaGetLastError());
                 FRK_CUDA(cudaMemcpyAsync(se + r0, dse.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
             }
             FRK_CUDA(cudaStreamSynchronize(st));
         }
+        mp->launches += derived.p->launches;
     });
 }
 

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <vector>
 #include "mrts_plan.cuh"
+#include "mrts_fit.cuh"
 
 namespace frk {
 
@@ -49,7 +50,8 @@ __global__ void pack_knots_kernel(const double* __restrict__ Xu, int64_t m, int 
 
 // cpoly[a*bn + col] = sum_j BBBH[a, j] * W[j, col0+col]   (src/autoFRK.cpp:324, (BBBH) * UZ.block(0,0,n,k))
 __global__ void cpoly_kernel(const double* __restrict__ BBBH, const double* __restrict__ UZ, int64_t ldu,
-                             int64_t m, int d, int col0, int ncols, int bn, double* __restrict__ cpoly) {
+                             int64_t m, int d, int col0, int ncols, int bn, const double* __restrict__ sub,
+                             double* __restrict__ cpoly) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (d + 1) * bn) return;
     const int a = idx / bn, col = idx % bn;
@@ -57,8 +59,32 @@ __global__ void cpoly_kernel(const double* __restrict__ BBBH, const double* __re
     if (col < ncols) {
         const double* w = UZ + int64_t(col0 + col) * ldu;
         for (int64_t j = 0; j < m; ++j) s = fma(BBBH[a + j * (d + 1)], w[j], s);
+        if (sub) s -= sub[a + int64_t(col0 + col) * (d + 1)];
     }
     cpoly[idx] = s;
+}
+
+// sub[0, j] = B[0, j] - sum_a shift_a / nconst_a * B[1+a, j];  sub[1+a, j] = B[1+a, j] / nconst_a
+// (the polynomial basis columns 1, (x_a - shift_a)/nconst_a of R/autoFRK.R:1462-1464 written as [1, x] %*% sub)
+__global__ void derive_sub_kernel(const double* __restrict__ B, int64_t ldb, int q, int d, double s0, double s1, double s2,
+                                  double c0, double c1, double c2, double* __restrict__ sub) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= q) return;
+    const double sh[3] = {s0, s1, s2}, nc[3] = {c0, c1, c2};
+    const double* b = B + int64_t(j) * ldb;
+    double v0 = b[0];
+    for (int a = 0; a < d; ++a) {
+        v0 -= sh[a] / nc[a] * b[1 + a];
+        sub[(1 + a) + int64_t(j) * (d + 1)] = b[1 + a] / nc[a];
+    }
+    sub[int64_t(j) * (d + 1)] = v0;
+}
+
+__global__ void copy_cols_kernel(const double* __restrict__ src, int64_t lds, int64_t rows, int cols, double* __restrict__ dst,
+                                 int64_t ldd) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i < rows && j < cols) dst[i + int64_t(j) * ldd] = src[i + int64_t(j) * lds];
 }
 
 __global__ void zero_columns_kernel(double* out, int64_t ldo, int64_t n2, int c0, int c1) {
@@ -92,7 +118,7 @@ const PredictKernelInfo* kernels_for(int d, int* count) {
 
 MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBBBH, const double* dUZ,
                           int64_t ldu, int k, const double* h_nconst, const double* h_shift,
-                          cudaStream_t st) {
+                          cudaStream_t st, const double* d_cpoly_sub, bool keep_sources) {
     if (d < 1 || d > 3) fail(1, "Unsupported dimension d: %d", d);
     if (m < 1) fail(1, "n must be greater than 1");
     if (k < 1) fail(1, "k must be positive");
@@ -121,6 +147,19 @@ MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBB
         int kc = k;
         while (kc > 0 && !flags[kc - 1]) --kc;
         p->k_compute = kc;
+        if (d_cpoly_sub) p->k_compute = kc = k;  // derived plan: the polynomial part alone can make a column non-zero
+        if (keep_sources) {
+            p->src_Xu.alloc(size_t(m) * d);
+            p->src_BBBH.alloc(size_t(d + 1) * m);
+            FRK_CUDA(cudaMemcpyAsync(p->src_Xu.p, dXu, sizeof(double) * m * d, cudaMemcpyDeviceToDevice, st));
+            FRK_CUDA(cudaMemcpyAsync(p->src_BBBH.p, dBBBH, sizeof(double) * (d + 1) * m, cudaMemcpyDeviceToDevice, st));
+            if (kc > 0) {
+                p->src_W.alloc(size_t(m) * kc);
+                dim3 grid(unsigned((m + 255) / 256), unsigned(kc));
+                copy_cols_kernel<<<grid, 256, 0, st>>>(dUZ, ldu, m, kc, p->src_W.p, m);
+                FRK_CUDA(cudaGetLastError());
+            }
+        }
         if (kc == 0) return p;  // nothing to project: X1 is identically zero
 
         // kernel configuration: smallest padded slice width that holds the columns
@@ -163,7 +202,7 @@ MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBB
             FRK_CUDA(cudaGetLastError());
             const int nthr = (d + 1) * best->bn;
             cpoly_kernel<<<(nthr + 127) / 128, 128, 0, st>>>(dBBBH, dUZ, ldu, m, d, sl.col0, sl.ncols, best->bn,
-                                                            sl.cpoly.p);
+                                                            d_cpoly_sub, sl.cpoly.p);
             FRK_CUDA(cudaGetLastError());
             p->slices.push_back(std::move(sl));
         }
@@ -176,6 +215,33 @@ MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBB
 }
 
 void plan_destroy(MrtsPlan* p) { delete p; }
+
+MrtsPlan* plan_derive_dev(MrtsPlan* p, const double* dB, int q, cudaStream_t st) {
+    if (!p->has_nconst) fail(1, "plan was created without nconst/shift: basis output unavailable");
+    if (!p->src_Xu.p) fail(2, "internal: plan keeps no sources to derive from");
+    if (q < 1) fail(1, "the coefficient matrix needs at least one column");
+    const int d = p->d, K = p->k;
+    const int kstar = K - d - 1;
+    if (kstar < 0) fail(1, "k-1 can not be smaller than the number of dimensions!");
+    const int kc = std::min(kstar, p->k_compute);
+    const int64_t m = p->m;
+    DevBuf<double> Wd(size_t(m) * q), sub(size_t(d + 1) * q);
+    if (kc > 0) {  // W' = W[:, 0:kc] %*% B[(d+1):(d+1+kc), ]
+        LinalgHandles& lh = linalg_handles();
+        FRK_CUBLAS(cublasSetStream(lh.blas, st));
+        const double one = 1.0, zero = 0.0;
+        FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(m), q, kc, &one, p->src_W.p, int(m), dB + (d + 1), K, &zero,
+                               Wd.p, int(m)));
+    } else {
+        FRK_CUDA(cudaMemsetAsync(Wd.p, 0, sizeof(double) * m * q, st));
+    }
+    derive_sub_kernel<<<(q + 127) / 128, 128, 0, st>>>(dB, K, q, d, p->shift[0], p->shift[1], p->shift[2], p->nconst[0],
+                                                      p->nconst[1], p->nconst[2], sub.p);
+    FRK_CUDA(cudaGetLastError());
+    MrtsPlan* out = plan_create_dev(p->src_Xu.p, m, d, p->src_BBBH.p, Wd.p, m, q, nullptr, nullptr, st, sub.p, false);
+    FRK_CUDA(cudaStreamSynchronize(st));  // Wd / sub are temporaries
+    return out;
+}
 
 // first `kout` columns of X1 into dout (columns past k_compute are exact zeros)
 static void predict_cols(MrtsPlan* p, const double* dxnew, int64_t n2, int64_t ldx, double* dout, int64_t ldo,

@@ -30,12 +30,21 @@ struct MrtsPlan {
     double nconst[3] = {1, 1, 1};  // attr(obj,"nconst")  R/autoFRK.R:1464
     bool has_nconst = false;
     int64_t launches = 0;   // kernels launched through this plan (bench bookkeeping)
+    // sources kept for derived plans (plan_derive_dev): knots m x d, BBBH (d+1) x m, W = UZ[0:m, 0:k_compute] (ld m)
+    DevBuf<double> src_Xu, src_BBBH, src_W;
 };
 
 // Inputs are DEVICE pointers, column-major: Xu m x d (ld m), BBBH (d+1) x m (ld d+1), UZ ld = ldu.
+// d_cpoly_sub (optional, (d+1) x k, ld d+1): subtracted from Cpoly = BBBH * W (derived plans).  keep_sources: keep
+// device copies of Xu, BBBH and W so that plan_derive_dev can be used on the plan.
 MrtsPlan* plan_create_dev(const double* dXu, int64_t m, int d, const double* dBBBH, const double* dUZ,
                           int64_t ldu, int k, const double* h_nconst, const double* h_shift,
-                          cudaStream_t st);
+                          cudaStream_t st, const double* d_cpoly_sub = nullptr, bool keep_sources = true);
+// Plan whose X1 output is basis(x) %*% B for a K x q coefficient matrix B (device, ld K; K = the plan's k, rows in
+// basis-column order [1, polynomial columns, X1 columns]): the projection W and the polynomial terms are folded
+// through B once (W' = W B_rest, m x q), so evaluating basis %*% B costs q columns of K1 instead of K columns plus
+// an n2 x K x q product, and the n2 x K basis is never formed.  Used for predict.FRK (R/autoFRK.R:1216,1220).
+MrtsPlan* plan_derive_dev(MrtsPlan* p, const double* dB, int q, cudaStream_t st);
 void plan_destroy(MrtsPlan* p);
 
 // X1 (n2 x k, ld ldo) on device from xnew (n2 x d, ld ldx) on device.  Columns >= k_compute are zero-filled.
