@@ -165,9 +165,11 @@ int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS,
                  double s, double ldet, int32_t wsave, int32_t only_loglik, int32_t has_vfixed, double vfixed,
                  double* v, double* negloglik, double* M, double* L, int32_t* nL);
 
-/* predict.FRK core (R/autoFRK.R:1216,1220) fused behind the basis evaluation: yhat = basis %*% w (n2 x T),
- * se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (n2; V, se may be NULL).  Host pointers; the n2 x K
- * basis never leaves the device. */
+/* predict.FRK core (R/autoFRK.R:1216,1220) fused into the basis evaluation: yhat = basis %*% w (n2 x T),
+ * se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (n2; V, se may be NULL; V symmetric, lower triangle read).
+ * Host pointers.  w and the eigen-factor R of V = R diag(+-1) R' are folded through the projection onto the knot
+ * eigenvectors (W' = W [w | R]), so one kernel pass with T + rank(V) columns produces both and the n2 x K basis
+ * is never formed; se^2 is accumulated as a signed sum of squares. */
 int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, const double* w, int32_t T,
                              const double* V, double* yhat, double* se);
 
