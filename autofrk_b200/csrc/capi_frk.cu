@@ -322,8 +322,9 @@ int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, con
         if (T < 1 || !w || !yhat) frk::fail(FRK_EINVAL, "w (K x T) and yhat (n2 x T) are required");
         cudaStream_t st = nullptr;
         const bool want_se = (V != nullptr && se != nullptr);
-        // Coefficient matrix B = [w | R] with V = R diag(sgn) R' (eigen-decomposition of V, |lambda| below
-        // 1e-15 max|lambda| dropped: that is below the rounding of the reference's own FP64 evaluation).  Then
+        // Coefficient matrix B = [w | R] with V = R diag(sgn) R' (eigen-decomposition of V; |lambda| <= K eps max|lambda|
+        // dropped -- the rank tolerance of LAPACK-style rank tests and the size of the rounding error of the
+        // reference's own FP64 evaluation of the bilinear form).  Then
         //   yhat = basis %*% w                                   R/autoFRK.R:1216
         //   se^2 = rowSums((basis %*% V) * basis) = sum_j sgn_j (basis %*% R)[, j]^2   R/autoFRK.R:1220
         // and basis %*% B comes straight out of K1 through a derived plan (W' = W B_rest): q = T + rank(V) columns
@@ -342,7 +343,7 @@ int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, con
             for (double l : lam_h) amax = std::fmax(amax, std::fabs(l));
             std::vector<int> keep;
             for (int i = K - 1; i >= 0; --i)
-                if (std::fabs(lam_h[i]) > 1e-15 * amax) keep.push_back(i);
+                if (std::fabs(lam_h[i]) > double(K) * 2.220446049250313e-16 * amax) keep.push_back(i);
             r = int(keep.size());
             dB.alloc(size_t(K) * (T + std::max(r, 1)));
             std::vector<double> scale(std::max(r, 1));

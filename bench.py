@@ -383,6 +383,21 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
                                                         else "NCCL all_reduce"),
         "note": "predict_gram = K1 (basis on the fly, 2 GB chunks) + K4 (Gram/cross-products); credited Gram flops "
                 f"{gram_flops:.3e} per GPU"}
+    if rank == 0:   # predict.FRK (yhat + se) at new locations with the fit above, first replicate: host buffers in and out
+        from autofrk_b200._lib import check as _check, lib as _l, ptr as _ptr
+        n_new = min(rows, 4_000_000)
+        xn = np.asfortranarray(xs[:n_new].cpu().numpy())
+        w1 = np.asfortranarray(res["w"][:, :1])
+        Vh = np.asfortranarray(res["V"])
+        yh, seh = np.empty((n_new, 1), order="F"), np.empty(n_new)
+        for _ in range(2):
+            t0 = time.perf_counter()
+            _check(_l.frk_plan_predict_frk(plan._h, _ptr(xn), n_new, _ptr(w1), 1, _ptr(Vh), _ptr(yh), _ptr(seh)))
+            t_pf = time.perf_counter() - t0
+        out["predict_FRK"] = {"locations": n_new, "K": K, "T": 1, "rank_V": int(np.linalg.matrix_rank(Vh)),
+                              "wall_ms": t_pf * 1e3, "locations_per_s": n_new / t_pf,
+                              "note": "w and the eigen-factor of V folded through the projection: one K1 pass with "
+                                      "1 + rank(V) columns, no n2 x K basis"}
     if rank == 0:
         from autofrk_b200 import frk as GF
         rng = np.random.default_rng(0)
