@@ -451,9 +451,17 @@ def main():
     ap.add_argument("--no-fit", action="store_true", help="skip the secondary fit timings")
     ap.add_argument("--fit-oracle", type=int, default=1, help="also time the CPU oracle's autoFRK at configs[0]")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: library chatter on fd 1 (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
-        return main_reference(args)
-    return main_gpu(args)
+        rc = main_reference(args)
+    else:
+        rc = main_gpu(args)
+    sys.stdout.flush()
+    return rc
 
 
 if __name__ == "__main__":
