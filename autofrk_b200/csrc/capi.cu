@@ -1,5 +1,6 @@
 // C ABI (include/frk_b200.h).  No exception crosses this boundary: everything is converted to
 // (status, thread-local message) -- the C analogue of BEGIN_RCPP/END_RCPP (src/RcppExports.cpp:18,24).
+#include <map>
 #include "capi_internal.cuh"
 
 namespace frk_capi {
@@ -19,9 +20,11 @@ void require_device() {
     }
 }
 
-frk::GramWorkspace& gram_workspace() {
-    static thread_local frk::GramWorkspace ws;
-    return ws;
+frk::GramWorkspace& gram_workspace() {  // one per host thread and device (the buffers live on that device)
+    static thread_local std::map<int, frk::GramWorkspace> ws;
+    int dev = 0;
+    FRK_CUDA(cudaGetDevice(&dev));
+    return ws[dev];
 }
 
 }  // namespace frk_capi

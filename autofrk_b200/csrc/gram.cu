@@ -322,7 +322,8 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         a.partial = ws.partial.p;
         const bool aligned = (reinterpret_cast<uintptr_t>(dF) % 16 == 0) && (ldf % 2 == 0) &&
                              (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));
-        static bool attr_set = false;
+        static bool attr_set_on[64] = {};  // the opt-in to large dynamic shared memory is per device
+        bool& attr_set = attr_set_on[dev & 63];
         if (!attr_set) {
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));

@@ -503,7 +503,10 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
 
     const CUtensorMap tmF = make_map(dF, n, K, ldf);
     const CUtensorMap tmZ = (T > 0) ? make_map(dZ, n, T, ldz) : tmF;
-    static bool attr_set = false;
+    static bool attr_set_on[64] = {};  // the opt-in to large dynamic shared memory is per device
+    int dev = 0;
+    FRK_CUDA(cudaGetDevice(&dev));
+    bool& attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));

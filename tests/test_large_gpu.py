@@ -84,3 +84,32 @@ def test_gram_additivity_and_trace_at_scale():
     fro = float((F[:n] ** 2).sum())
     assert abs(float(torch.trace(Gm)) - fro) / fro < 1e-12
     assert abs(float(whole[-1]) - float((Z[:n] ** 2).sum())) / float(whole[-1]) < 1e-12
+
+
+def test_second_device_in_one_process():
+    """frk_set_device(1) after work on device 0: plans, workspaces, cuSOLVER handles and shared-memory opt-ins are
+    per device.  Needs two visible GPUs (skipped on a one-GPU box)."""
+    from autofrk_b200 import _lib, frk as G, mrts as GM
+
+    if _lib.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    rng = np.random.default_rng(2)
+    Xu = rng.random((300, 2))
+    x = rng.random((5000, 2))
+    F0 = Z = None
+    results = []
+    try:
+        for dev in (0, 1):
+            _lib.check(_lib.lib.frk_set_device(dev))
+            basis = GM.mrts(Xu, 60)
+            F = GM.predict_mrts(basis, x)
+            if F0 is None:
+                F0 = F
+                Z = F[:, :4] @ rng.standard_normal((4, 3)) + rng.standard_normal((5000, 3))
+            Gm, Cm, zz = G.gram_stats(np.asfortranarray(np.hstack([F, F, F])), Z)     # K = 180: the tensor-core job kernel
+            fit = G.cMLEimat(F, Z, 0.0, wSave=True)
+            results.append((F, Gm, Cm, zz, fit["M"], fit["w"]))
+    finally:
+        _lib.check(_lib.lib.frk_set_device(0))
+    for a, b in zip(results[0], results[1]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))      # same code, same inputs: bitwise equal across devices
