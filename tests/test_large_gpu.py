@@ -55,6 +55,50 @@ def test_int64_indexing_and_row_equivariance():
     torch.cuda.empty_cache()
 
 
+def test_config3_full_size_3d():
+    """BASELINE configs[2] at full size -- 2,000 3-D knots, K = 1,000 (k* = 996, two column slices), 10 M locations,
+    80 GB of basis on one GPU -- through properties that need no oracle: knots planted among the locations reproduce
+    the fitted basis (predict(mrts(knot, k), knot) == mrts(knot, k)), far rows equal the same rows evaluated alone
+    (64-bit indexing: 1e10 elements), and the polynomial columns are exact."""
+    import torch
+    from autofrk_b200 import mrts as G
+    from autofrk_b200._lib import FRK_OUT_BASIS
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs ~85 GB of free device memory")
+    rng = np.random.default_rng(3)
+    d, m, K = 3, 2000, 1000
+    Xu = rng.random((m, d))
+    basis = G.mrts(Xu, K)
+    plan = basis.plan()
+    n2 = 10_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=g).T
+    spots = torch.tensor([0, 4_999_999, n2 - m], device="cuda")          # plant the knots at three offsets
+    Xu_t = torch.from_numpy(Xu).cuda()
+    for s0 in spots.tolist():
+        x[s0:s0 + m] = Xu_t
+    out = torch.empty((K, n2), dtype=torch.float64, device="cuda").T
+    plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
+    torch.cuda.synchronize()
+    X = torch.from_numpy(np.ascontiguousarray(basis.X)).cuda()
+    scale = X.abs().amax(dim=0)
+    for s0 in spots.tolist():
+        err = ((out[s0:s0 + m] - X).abs().amax(dim=0) / scale).max().item()
+        assert err < 1e-9, (s0, err)                                       # fit-vs-predict identity (SURVEY.md section 4)
+    assert torch.equal(out[s0:s0 + m], out[0:m])                           # same rows, same values wherever they sit
+    tail = slice(n2 - 3000, n2 - m)
+    sub = torch.empty((K, tail.stop - tail.start), dtype=torch.float64, device="cuda").T
+    plan.predict_dev(x[tail].T.contiguous().T, sub, mode=FRK_OUT_BASIS)
+    assert torch.equal(out[tail], sub)
+    assert torch.all(out[:, 0] == 1.0)
+    shift, nconst = torch.from_numpy(Xu.mean(axis=0)).cuda(), torch.from_numpy(np.asarray(basis.nconst)).cuda()
+    assert ((out[:100_000, 1:1 + d] - (x[:100_000] - shift) / nconst).abs().max().item()) < 1e-13
+    del out, sub, x
+    torch.cuda.empty_cache()
+
+
 def test_gram_additivity_and_trace_at_scale():
     """2M x 500 basis: Gram of the whole equals the sum over three ragged row shards; trace(G) = ||F||_F^2."""
     import ctypes as C
