@@ -371,27 +371,81 @@ int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, con
             ~PlanGuard() { frk::plan_destroy(p); }
         } derived{frk::plan_derive_dev(mp, dB.p, q, st)};
 
-        int64_t rc = std::min<int64_t>(n2, default_chunk_rows(derived.p, q));
-        frk::DevBuf<double> dx(size_t(n2) * d), dy(size_t(rc) * q), dse, dsgn;
-        FRK_CUDA(cudaMemcpyAsync(dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, st));
+        // Row chunks, software-pipelined on two streams: while chunk c runs through K1 (+ the se reduction), the
+        // coordinates of chunk c+1 go up and the results of chunk c-1 come down.  Copies from / to pageable host
+        // memory block the host thread, so the next chunk's kernels are always queued before a copy is issued.
+        plan->ensure_streams();
+        cudaStream_t sc = plan->s_comp, sx = plan->s_copy;
+        const int64_t bm = derived.p->ki ? derived.p->ki->bm : 128;
+        const int64_t wave = bm * derived.p->sm_count;
+        int64_t rc = std::max<int64_t>(wave, ((int64_t(256) << 20) / (int64_t(q + d) * 8)) / wave * wave);
+        rc = std::min(rc, n2);
+        if (rc % 2) ++rc;
+        const int nchunk = int((n2 + rc - 1) / rc);
+        frk::DevBuf<double> dx[2], dy[2], dse[2], dsgn;
+        for (int b2 = 0; b2 < 2; ++b2) {
+            dx[b2].alloc(size_t(rc) * d);
+            dy[b2].alloc(size_t(rc) * q);
+            if (want_se) dse[b2].alloc(static_cast<size_t>(rc));
+        }
         if (want_se) {
-            dse.alloc(static_cast<size_t>(rc));
             dsgn.alloc(static_cast<size_t>(std::max(r, 1)));
-            if (r > 0) FRK_CUDA(cudaMemcpyAsync(dsgn.p, sgn.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
+            if (r > 0) FRK_CUDA(cudaMemcpyAsync(dsgn.p, sgn.data(), sizeof(double) * r, cudaMemcpyHostToDevice, sc));
         }
-        for (int64_t r0 = 0; r0 < n2; r0 += rc) {
-            const int64_t rows = std::min(rc, n2 - r0);
-            frk::plan_predict_x1_dev(derived.p, dx.p + r0, rows, n2, dy.p, rc, st);
-            FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n2, dy.p, sizeof(double) * rc, sizeof(double) * rows,
-                                       size_t(T), cudaMemcpyDeviceToHost, st));
-            if (want_se) {
-                signed_rownorm_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dy.p + size_t(rc) * T, rows, rc, r, dsgn.p,
-                                                                                   dse.p);
-                FRK_CUDA(cudaGetLastError());
-                FRK_CUDA(cudaMemcpyAsync(se + r0, dse.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+        cudaEvent_t ev_up[2], ev_done[2], ev_down[2];
+        for (int b2 = 0; b2 < 2; ++b2) {
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_up[b2], cudaEventDisableTiming));
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_done[b2], cudaEventDisableTiming));
+            FRK_CUDA(cudaEventCreateWithFlags(&ev_down[b2], cudaEventDisableTiming));
+        }
+        struct EvGuard {
+            cudaEvent_t* e[3];
+            ~EvGuard() {
+                for (auto* arr : e)
+                    for (int i = 0; i < 2; ++i) cudaEventDestroy(arr[i]);
             }
-            FRK_CUDA(cudaStreamSynchronize(st));
+        } evguard{{ev_up, ev_done, ev_down}};
+        auto rows_of = [&](int c) { return std::min(rc, n2 - int64_t(c) * rc); };
+        auto upload = [&](int c) {   // coordinates of chunk c -> dx[c & 1] (d column pieces of the n2 x d matrix)
+            const int b2 = c & 1;
+            if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(sx, ev_done[b2], 0));   // chunk c-2 has consumed this buffer
+            FRK_CUDA(cudaMemcpy2DAsync(dx[b2].p, sizeof(double) * rc, xnew + int64_t(c) * rc, sizeof(double) * n2,
+                                       sizeof(double) * rows_of(c), size_t(d), cudaMemcpyHostToDevice, sx));
+            FRK_CUDA(cudaEventRecord(ev_up[b2], sx));
+        };
+        auto compute = [&](int c) {
+            const int b2 = c & 1;
+            const int64_t rows = rows_of(c);
+            FRK_CUDA(cudaStreamWaitEvent(sc, ev_up[b2], 0));
+            if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(sc, ev_down[b2], 0));   // results of chunk c-2 have left dy / dse
+            frk::plan_predict_x1_dev(derived.p, dx[b2].p, rows, rc, dy[b2].p, rc, sc);
+            if (want_se) {
+                signed_rownorm_kernel<<<unsigned((rows + 255) / 256), 256, 0, sc>>>(dy[b2].p + size_t(rc) * T, rows, rc, r, dsgn.p,
+                                                                                   dse[b2].p);
+                FRK_CUDA(cudaGetLastError());
+            }
+            FRK_CUDA(cudaEventRecord(ev_done[b2], sc));
+        };
+        auto download = [&](int c) {
+            const int b2 = c & 1;
+            const int64_t rows = rows_of(c), r0 = int64_t(c) * rc;
+            FRK_CUDA(cudaStreamWaitEvent(sx, ev_done[b2], 0));
+            FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n2, dy[b2].p, sizeof(double) * rc, sizeof(double) * rows,
+                                       size_t(T), cudaMemcpyDeviceToHost, sx));
+            if (want_se) FRK_CUDA(cudaMemcpyAsync(se + r0, dse[b2].p, sizeof(double) * rows, cudaMemcpyDeviceToHost, sx));
+            FRK_CUDA(cudaEventRecord(ev_down[b2], sx));
+        };
+        upload(0);
+        compute(0);
+        for (int c = 0; c < nchunk; ++c) {
+            if (c + 1 < nchunk) {
+                upload(c + 1);
+                compute(c + 1);
+            }
+            download(c);
         }
+        FRK_CUDA(cudaStreamSynchronize(sc));
+        FRK_CUDA(cudaStreamSynchronize(sx));
         mp->launches += derived.p->launches;
     });
 }

@@ -449,6 +449,8 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
 // <D, WR, WC, MT, NT, KC, NSTAGE>: KC chosen so that every thread evaluates a whole number of Phi
 // values per chunk (BM*KC is a multiple of the thread count)
 #define FRK_PREDICT_CONFIG_TABLE(D)                                                                        \
+    predict_info<PredictCfg<D, 16, 1, 4, 1, 8, 4>>(),  /* BM 512, BN   8: Phi-bound (predict.FRK, T = 1)  */  \
+    predict_info<PredictCfg<D, 8, 2, 4, 1, 16, 4>>(),  /* BM 256, BN  16 */                                \
     predict_info<PredictCfg<D, 4, 4, 4, 1, 32, 4>>(),  /* BM 128, BN  32, 8 Phi/thread */                  \
     predict_info<PredictCfg<D, 4, 4, 4, 2, 32, 4>>(),  /* BM 128, BN  64 */                                \
     predict_info<PredictCfg<D, 4, 4, 4, 3, 16, 4>>(),  /* BM 128, BN  96 */                                \
