@@ -22,12 +22,13 @@
 //     mbarriers, so warps drift up to a chunk apart and the pipe does not drain at chunk boundaries.
 //   * persistent CTAs (one per SM), tiles of BM rows dealt round-robin.
 #pragma once
+#include <cstdlib>
 #include "frk_common.cuh"
 #include "tps_log_table.h"
 
 namespace frk {
 
-template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_>
+template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_, int AHEAD_ = 2>
 struct PredictCfg {
     static constexpr int D = D_, WR = WR_, WC = WC_, MT = MT_, NT = NT_, KC = KC_, NSTAGE = NSTAGE_;
     static constexpr int DP = (D == 3) ? 4 : D;   // doubles per stored coordinate tuple
@@ -42,16 +43,16 @@ struct PredictCfg {
     static constexpr int PHI_DOUBLES = BM * KC;
     static constexpr int XS_DOUBLES = BM * DP;
     static constexpr int LOGTAB_DOUBLES = (D == 2) ? 2 * kLogTabSize : 0;
-    static constexpr int AHEAD = 2;               // Phi is produced this many chunks ahead of its DMMAs
-    static constexpr int NPB = 4;                 // Phi chunk buffers (>= 2 * AHEAD)
-    static constexpr int MIN_CHUNKS = 4;          // the plan pads the knot list to at least this many chunks
+    static constexpr int AHEAD = AHEAD_;          // Phi is produced this many chunks ahead of its DMMAs
+    static constexpr int NPB = 2 * AHEAD;         // Phi chunk buffers (>= 2 * AHEAD)
+    static constexpr int MIN_CHUNKS = (2 * AHEAD > 4) ? 2 * AHEAD : 4;  // the plan pads the knot list to at least this many chunks
     static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + NPB * PHI_DOUBLES * 8 + 2 * XS_DOUBLES * 8 +
                                          LOGTAB_DOUBLES * 8 + (NSTAGE + NPB) * 8 + NSTAGE * 4 + 16;
     static_assert(KC % 4 == 0, "KC must be a multiple of the DMMA k (4)");
     static_assert(STAGE_BYTES % 16 == 0, "TMA bulk copies need 16 B multiples");
     static_assert(NTHREADS <= 1024, "too many warps");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-    static_assert(NPB == 4 && AHEAD == 2, "the Phi ring uses pb ^ AHEAD");
+    static_assert(NPB >= 2 * AHEAD && MIN_CHUNKS >= 2 * AHEAD, "Phi ring depth");
 };
 
 struct PredictArgs {
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     uint32_t wpar = 0;
     int pb = 0;             // Phi buffer of the current chunk, parity of its use
     uint32_t ppar = 0;
+    int pbw = AHEAD % NPB;  // Phi buffer written this iteration: (pb + AHEAD) mod NPB
     int cphi = AHEAD % nchunks;            // chunk (within its tile) whose Phi is produced this iteration
     int cref = NSTAGE % nchunks;           // chunk that refills the stage released this iteration
     int left = int(total);                 // iterations still to run, including this one (host checks < 2^31)
@@ -376,12 +378,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                     okw = mbar_test_wait(&w_full[sn], wparn);
                 }
             }
-            // (4) hand Phi(it+AHEAD) over.  Its buffer (pb ^ 2, NPB = 4) was last read by the DMMAs of chunk
+            // (4) hand Phi(it+AHEAD) over.  Its buffer ((pb + AHEAD) mod NPB, NPB = 2 AHEAD) was last read by the DMMAs of chunk
             //     it+AHEAD-NPB, which every warp finished before (1) could pass.
-            if (more) phi_store(pb ^ AHEAD, val);
+            if (more) phi_store(pbw, val);
             __syncwarp();
             if (lane == 0) {
-                if (more) mbar_arrive(&phi_full[pb ^ AHEAD]);
+                if (more) mbar_arrive(&phi_full[pbw]);
                 // (5) the last warp to finish with W stage s refills it for chunk it + NSTAGE
                 if (smem_add_relaxed(&w_done[s], 1u) == uint32_t(NWARPS - 1)) {
                     w_done[s] = 0;
@@ -396,6 +398,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
             wpar = wparn;
             pb = pbn;
             ppar = pparn;
+            pbw = (pbw + 1 == NPB) ? 0 : pbw + 1;
             cphi = (cphi + 1 == nchunks) ? 0 : cphi + 1;
             cref = (cref + 1 == nchunks) ? 0 : cref + 1;
             --left;
@@ -426,14 +429,23 @@ struct PredictKernelInfo {
     void (*prepare)();  // opt in to large dynamic shared memory (once)
 };
 
+#ifdef FRK_EXPERIMENTAL_CONFIGS   // FRK_SMEM_PAD=<bytes>: extra (unused) dynamic shared memory, shrinks the L1 carve-out
+inline size_t predict_smem_pad(size_t base) {
+    const char* e = std::getenv("FRK_SMEM_PAD");
+    const size_t pad = e ? size_t(std::atol(e)) : 0;
+    return (base + pad <= 227 * 1024) ? pad : 0;
+}
+#else
+inline size_t predict_smem_pad(size_t) { return 0; }
+#endif
 template <class C>
 void predict_prepare() {
     FRK_CUDA(cudaFuncSetAttribute(mrts_predict_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(C::SMEM_BYTES)));
+                                  int(C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES))));
 }
 template <class C>
 void predict_launch(const PredictArgs& a, int grid, cudaStream_t st) {
-    mrts_predict_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES, st>>>(a);
+    mrts_predict_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES), st>>>(a);
 }
 template <class C>
 constexpr PredictKernelInfo predict_info() {
@@ -458,10 +470,23 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 2, 8, 4, 3, 16, 4>>(),  /* BM  64, BN 192, 2 Phi/thread */                  \
     predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>(),  /* BM  96, BN 200, 4 Phi/thread, 15 warps */        \
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
-    predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 4>>(),  /* BM  64, BN 320 */                                \
-    predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4>>(), /* BM  32, BN 384, 1 Phi/thread */                  \
-    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3>>(), /* BM  32, BN 512, 1 Phi/thread, 3 x 66 KB stages */          \
+    predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>(), /* BM  64, BN 320, Phi 3 ahead */                  \
+    predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3>>(), /* BM  32, BN 384, 1 Phi/thread, Phi 3 ahead */  \
+    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>(), /* BM  32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead */ \
     predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>(),  /* BM  32, BN 512, 8 fat warps (32 x 64 tiles), experimental */ \
-    predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()   /* BM  64, BN 200, 20 thin warps, 2 Phi/thread, experimental */
+    predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()   /* BM  64, BN 200, 20 thin warps, 2 Phi/thread, experimental */ \
+    FRK_PREDICT_EXTRA_CONFIGS(D)
+#ifdef FRK_EXPERIMENTAL_CONFIGS   // Phi ring depth study (tools/k1_cfg_probe.py with FRK_K1_CONFIG)
+#define FRK_PREDICT_EXTRA_CONFIGS(D)                                                                       \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 14: BN 512, 3 stages, AHEAD 2 (round-1 v6) */  \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 2, 2>>() /* 15: BN 384 */                                 \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 2, 3>>() /* 16 */                                         \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3>>() /* 17 */                                         \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 2>>() /* 18 */                                         \
+    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 2, 3>>()  /* 19: BN 320 */                                 \
+    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>()  /* 20 */
+#else
+#define FRK_PREDICT_EXTRA_CONFIGS(D)
+#endif
 
 }  // namespace frk
