@@ -472,19 +472,17 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
     predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>(), /* BM  64, BN 320, Phi 3 ahead */                  \
     predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3>>(), /* BM  32, BN 384, 1 Phi/thread, Phi 3 ahead */  \
-    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>(), /* BM  32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead */ \
-    predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>(),  /* BM  32, BN 512, 8 fat warps (32 x 64 tiles), experimental */ \
-    predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()   /* BM  64, BN 200, 20 thin warps, 2 Phi/thread, experimental */ \
+    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>()  /* BM  32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead */ \
     FRK_PREDICT_EXTRA_CONFIGS(D)
 #ifdef FRK_EXPERIMENTAL_CONFIGS   // Phi ring depth study (tools/k1_cfg_probe.py with FRK_K1_CONFIG)
 #define FRK_PREDICT_EXTRA_CONFIGS(D)                                                                       \
-    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 14: BN 512, 3 stages, AHEAD 2 (round-1 v6) */  \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 2, 2>>() /* 15: BN 384 */                                 \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 2, 3>>() /* 16 */                                         \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3>>() /* 17 */                                         \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 2>>() /* 18 */                                         \
-    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 2, 3>>()  /* 19: BN 320 */                                 \
-    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>()  /* 20 */
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 12: BN 512, 3 stages, AHEAD 2 (v6) */         \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 2>>() /* 13: BN 512, 2 stages, AHEAD 2 */              \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 4>>() /* 14: BN 512, 2 stages, AHEAD 4 */              \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4, 2>>() /* 15: BN 384, 4 stages, AHEAD 2 (v6) */         \
+    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 4, 2>>()  /* 16: BN 320, 4 stages, AHEAD 2 (v6) */         \
+    , predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()     /* 17: BN 512, 8 fat warps (32 x 64 tiles) */     \
+    , predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()     /* 18: BN 200, 20 thin warps, 2 Phi/thread */
 #else
 #define FRK_PREDICT_EXTRA_CONFIGS(D)
 #endif

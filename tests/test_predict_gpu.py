@@ -32,6 +32,10 @@ CASES = [
     (3, 700, 520, 1500),
     (1, 30, 8, 999),
     (1, 40, 10, 31),
+    (2, 150, 3, 2500),      # BN 8 configuration (512-row tiles)
+    (3, 120, 12, 1111),     # BN 16
+    (2, 900, 380, 1500),    # BN 384, Phi three chunks ahead
+    (2, 700, 310, 900),     # BN 320
 ]
 
 
@@ -158,7 +162,8 @@ def test_output_guard_bands_untouched():
 
     rng = np.random.default_rng(12)
     sentinel = -7.25
-    for d, m, kstar, n2 in [(2, 90, 28, 1001), (2, 400, 197, 3333), (2, 700, 497, 2047), (3, 300, 600, 1500), (1, 50, 9, 77)]:
+    for d, m, kstar, n2 in [(2, 90, 28, 1001), (2, 400, 197, 3333), (2, 700, 497, 2047), (3, 300, 600, 1500), (1, 50, 9, 77),
+                            (2, 120, 5, 999), (3, 64, 8, 515), (2, 800, 380, 1027), (2, 700, 310, 640), (2, 20, 2, 3000)]:
         Xu = rng.random((m, d))
         UZ = np.zeros((m + d + 1, kstar + d + 1))
         UZ[:m, :kstar] = rng.standard_normal((m, kstar))
