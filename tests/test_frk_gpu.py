@@ -446,3 +446,50 @@ def test_gram_narrow_variant(n, K, T, weighted):
         assert abs(packed[-1].item() - zz) / zz < 1e-12
     else:
         assert packed[-1].item() == 0.0
+
+
+def test_plan_predict_frk_folded_path_edge_cases():
+    """frk_plan_predict_frk (coefficients folded through the projection) against the explicit products
+    basis %*% w and sqrt(pmax(0, rowSums((basis %*% V) * basis))) (R/autoFRK.R:1216,1220): indefinite V (the signed sum
+    of squares must reproduce the clamped bilinear form), full-rank V, zero V, no V, one location, many replicates,
+    chunked pipeline (n2 above one chunk), d = 1 and d = 3."""
+    import ctypes as C
+    from autofrk_b200 import _lib, mrts as GM
+
+    rng = np.random.default_rng(31)
+
+    def run(basis, x, w, V):
+        n2, T = x.shape[0], w.shape[1]
+        yhat = np.empty((n2, T), order="F")
+        se = None if V is None else np.empty(n2)
+        _lib.check(_lib.lib.frk_plan_predict_frk(basis.plan()._h, _lib.ptr(x), n2, _lib.ptr(w), T,
+                                                 None if V is None else _lib.ptr(V), _lib.ptr(yhat),
+                                                 None if se is None else _lib.ptr(se)))
+        return yhat, se
+
+    for d, m, K, n2, T in ((2, 200, 40, 3001, 3), (1, 60, 12, 1, 1), (3, 150, 30, 777, 5), (2, 120, 25, 400_000, 2)):
+        basis = GM.mrts(rng.random((m, d)), K)
+        x = np.asfortranarray(rng.random((n2, d)))
+        F = GM.predict_mrts(basis, x) if n2 <= 5000 else None
+        w = np.asfortranarray(rng.standard_normal((K, T)))
+        R = rng.standard_normal((K, 3))
+        cases = {"psd_rank3": R @ R.T, "full_rank": (lambda A: A @ A.T)(rng.standard_normal((K, K))),
+                 "indefinite": R @ np.diag([1.0, -2.0, 0.5]) @ R.T, "zero": np.zeros((K, K)), "none": None}
+        for name, V in cases.items():
+            Vf = None if V is None else np.asfortranarray(V)
+            yhat, se = run(basis, x, w, Vf)
+            if F is None:                                         # large n2: check three scattered row blocks
+                idx = np.r_[0:500, n2 // 2:n2 // 2 + 500, n2 - 500:n2]
+                Fi = GM.predict_mrts(basis, np.asfortranarray(x[idx]))
+            else:
+                idx, Fi = np.arange(n2), F
+            ref_y = Fi @ w
+            assert np.abs(yhat[idx] - ref_y).max() <= 1e-11 * max(1.0, np.abs(ref_y).max()), (d, name)
+            if V is not None:
+                q = np.sum((Fi @ V) * Fi, axis=1)
+                ref_se = np.sqrt(np.maximum(0.0, q))
+                scale = max(1e-300, np.abs(q).max())
+                # compare squares: where the bilinear form is clamped at 0 the reference's own rounding decides the sign
+                assert np.abs(se[idx] ** 2 - ref_se ** 2).max() <= 1e-10 * scale, (d, name)
+                if name == "zero":
+                    assert np.all(se == 0.0)
