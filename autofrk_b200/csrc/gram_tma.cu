@@ -9,8 +9,10 @@
 //     F x Z tiles of the same blocks), so no DMMA is spent on a lower triangle or on padding beyond 31 columns.
 //     The 128-column tiling this replaces spent 200 warp tiles on K = 500, T = 1 (now 152) and 68 on K = 200,
 //     T = 20 (now 35);
-//   * a job with <= 8 (<= 4) tiles runs every tile on 2 (4) warps that take alternate k4-steps, so small shapes
-//     still occupy all four SM sub-partitions; the reduction adds those partials like further row splits;
+//   * inside a job the unit of work is (tile, set of k4-steps): tiles are dealt to the four SM sub-partitions
+//     heaviest first, and while warps are free part of a tile's k4-steps moves from the busiest sub-partition to
+//     the idlest one (a 10-tile diagonal job runs as 2.5 tile-times per sub-partition instead of 3,3,2,2; a job
+//     with few tiles still occupies all four); the reduction adds a split tile's partials like further row splits;
 //   * slots arrive by cp.async.bulk.tensor.2d (UTMALDG) with SWIZZLE_128B into dense [column][16 rows] boxes;
 //     the MMA k index is permuted (rows 2q, 2q+1, 2q+8, 2q+9 form k4-step q) so that every fragment LDS.64 is
 //     bank-conflict free under that swizzle; out-of-range rows / columns are zero-filled by the TMA unit;
@@ -47,10 +49,13 @@ constexpr size_t SMEM_BYTES = size_t(NST) * STAGE_BYTES + 1024 /* alignment slac
 
 // one job: column blocks to stage (F blocks are < kb, Z blocks follow) and the block pairs computed from them
 struct GramJob {
-    int nslots, ntiles, kgroups;     // kgroups warps share a tile, taking alternate k4-steps
+    int nslots, ntiles, nactive;     // staged blocks, output tiles, warps with work
     int slot_block[MAXSLOTS];
-    unsigned char slot_a[NWARPS], slot_b[NWARPS];
-    unsigned char ntn[NWARPS];       // 8-column groups of block b that hold real columns (1..4)
+    // per warp: the tile it works on, the k4-steps of every stage it takes (bit q of qmask; 0 = idle warp),
+    // and how many 8-column groups of block b hold real columns (1..4)
+    unsigned char w_tile[NWARPS], qmask[NWARPS], ntn[NWARPS];
+    // per tile: its two staged blocks and the warps whose partial sums make it up
+    unsigned char slot_a[NWARPS], slot_b[NWARPS], tile_nw[NWARPS], tile_w[NWARPS][4];
 };
 
 struct GramTmaArgs {
@@ -114,15 +119,13 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         const int jid = item % a.njobs;
         const GramJob* const job = a.jobs + jid;
         const int nslots = __ldg(&job->nslots);
-        const int ntiles = __ldg(&job->ntiles);
-        const int kgroups = __ldg(&job->kgroups);
-        const int nactive = ntiles * kgroups;
-        const bool active = warp < nactive;
-        const int tile = active ? warp % ntiles : 0;
-        const int kg = active ? warp / ntiles : 0;
+        const int nactive = __ldg(&job->nactive);
+        const int qmask = __ldg(&job->qmask[warp]);
+        const bool active = qmask != 0;
+        const int tile = __ldg(&job->w_tile[warp]);
         const int sa = __ldg(&job->slot_a[tile]);
         const int sb = __ldg(&job->slot_b[tile]);
-        const int ntn = __ldg(&job->ntn[tile]);
+        const int ntn = __ldg(&job->ntn[warp]);
         // the slot this lane copies when its warp re-arms a stage
         const int my_block = (lane < nslots) ? __ldg(&job->slot_block[lane]) : 0;
         const CUtensorMap* const my_tm = (my_block < a.kb) ? &tmF : &tmZ;
@@ -163,12 +166,12 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             };
             if (WEIGHTED && nsteps > 0) load_w(0);
             double wcur[4];
-            // k4-steps q0, q0+dq, ... of one stage on the first NTN 8-column groups of block b
-            auto ksteps = [&](const unsigned char* As, auto ntn_c, int q0, int dq) {
+            // this warp's k4-steps of one stage on the first NTN 8-column groups of block b
+            auto ksteps = [&](const unsigned char* As, auto ntn_c) {
                 constexpr int NTN = decltype(ntn_c)::value;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (dq != 1 && (q & (dq - 1)) != q0) continue;
+                    if (!((qmask >> q) & 1)) continue;   // warp-uniform
                     double af[4], bf[NTN];
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) af[mt] = *reinterpret_cast<const double*>(As + a_line + mt * 1024 + off[q]);
@@ -195,18 +198,13 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 #pragma unroll
                 for (int q = 0; q < 4; ++q) wcur[q] = wq[q];
                 if (WEIGHTED && step + 1 < nsteps) load_w(step + 1);
-                if (kgroups == 1) {
-                    switch (ntn) {  // warp-uniform: real branches, never predicated-off DMMAs
-                        case 1: ksteps(As, std::integral_constant<int, 1>{}, 0, 1); break;
-                        case 2: ksteps(As, std::integral_constant<int, 2>{}, 0, 1); break;
-                        case 3: ksteps(As, std::integral_constant<int, 3>{}, 0, 1); break;
-                        default: ksteps(As, std::integral_constant<int, 4>{}, 0, 1); break;
-                    }
-                    if (step + 1 < nsteps) ok = mbar_test_wait(&full[lsn], lparn);
-                } else {
-                    ksteps(As, std::integral_constant<int, 4>{}, kg, kgroups);
-                    ok = false;
+                switch (ntn) {  // warp-uniform: real branches, never predicated-off DMMAs
+                    case 1: ksteps(As, std::integral_constant<int, 1>{}); break;
+                    case 2: ksteps(As, std::integral_constant<int, 2>{}); break;
+                    case 3: ksteps(As, std::integral_constant<int, 3>{}); break;
+                    default: ksteps(As, std::integral_constant<int, 4>{}); break;
                 }
+                if (step + 1 < nsteps) ok = mbar_test_wait(&full[lsn], lparn);
                 __syncwarp();
                 uint32_t last = 0;
                 if (lane == 0) last = (smem_add_relaxed(&done[ls], 1u) == uint32_t(nactive - 1)) ? 1u : 0u;
@@ -246,7 +244,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 }
 
 // add the partial tiles in a fixed order and scatter into packed = [G (K x K) | C (K x T) | zz].
-// One block per (job, tile, 64-element slice); its four thread groups each add every fourth (row split, k-group)
+// One block per (job, tile, 64-element slice); its four thread groups each add every fourth (row split, warp)
 // partial in order and the four sums are combined as (s0 + s1) + (s2 + s3): the same order on every run.
 constexpr int RED_ELEMS = 64, RED_GROUPS = 4;
 __global__ void __launch_bounds__(RED_ELEMS * RED_GROUPS)
@@ -256,7 +254,7 @@ gram_tma_reduce_kernel(const GramTmaArgs a, const double* __restrict__ zzpart, i
     const int tile = (blockIdx.x / SLICES) % NWARPS;
     const int jid = blockIdx.x / (SLICES * NWARPS);
     const GramJob* const job = a.jobs + jid;
-    const int ntiles = job->ntiles, kgroups = job->kgroups;
+    const int ntiles = job->ntiles;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double s = 0.0;
         for (int i = 0; i < nzz; ++i) s += zzpart[i];
@@ -274,10 +272,11 @@ gram_tma_reduce_kernel(const GramTmaArgs a, const double* __restrict__ zzpart, i
     __shared__ double sh[RED_GROUPS][RED_ELEMS];
     double s = 0.0;
     if (wanted) {
-        const int nparts = a.nsplit * kgroups;
+        const int nw = job->tile_nw[tile];
+        const int nparts = a.nsplit * nw;
         for (int p = grp; p < nparts; p += RED_GROUPS) {
-            const int sp = p / kgroups, k = p % kgroups;
-            s += a.partial[((size_t(sp) * a.njobs + jid) * NWARPS + tile + k * ntiles) * TILE_DOUBLES + e];
+            const int sp = p / nw, wv = job->tile_w[tile][p % nw];
+            s += a.partial[((size_t(sp) * a.njobs + jid) * NWARPS + wv) * TILE_DOUBLES + e];
         }
     }
     sh[grp][threadIdx.x % RED_ELEMS] = s;
@@ -425,34 +424,93 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
             d = GramJob{};
             d.nslots = int(h.blocks.size());
             d.ntiles = int(h.tiles.size());
-            d.kgroups = d.ntiles <= 4 ? 4 : (d.ntiles <= 8 ? 2 : 1);
             for (int i = 0; i < d.nslots; ++i) d.slot_block[i] = h.blocks[i];
-            // warp i runs on SM sub-partition i % 4: hand the tiles out heaviest first (cost = valid 8-column
-            // groups of block b) to the sub-partition with the least work that still has a free warp
-            std::vector<int> cost(d.ntiles), order(d.ntiles), warp_of(d.ntiles);
+            // Work units: (tile, set of k4-steps).  Warp i runs on SM sub-partition i % 4, at most four warps each.
+            // Cost of a unit = valid 8-column groups of block b x k4-steps.  Whole tiles go out heaviest first to
+            // the least loaded sub-partition; then, while a warp is free, part of a unit moves from the busiest
+            // sub-partition to the idlest one (a tile split over warps is added up by the reduction kernel), so
+            // e.g. the 10 tiles of a diagonal macro tile cost 2.5 tile-times per sub-partition instead of 3,3,2,2.
+            struct Unit { int tile, cost, mask, sp; };
+            std::vector<Unit> units;
+            std::vector<int> order(d.ntiles);
             for (int i = 0; i < d.ntiles; ++i) {
                 const int bb = h.tiles[i].second;
                 const int valid = std::min(CB, bb < a.kb ? K - bb * CB : T - (bb - a.kb) * CB);
-                cost[i] = (valid + 7) / 8;
+                units.push_back({i, (valid + 7) / 8, 0xF, -1});
                 order[i] = i;
+                d.slot_a[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].first) - h.blocks.begin());
+                d.slot_b[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].second) - h.blocks.begin());
             }
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return units[x].cost > units[y].cost; });
             int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            auto nq = [](int mask) { return __builtin_popcount(unsigned(mask)); };
             for (int i : order) {
                 int best = -1;
-                for (int sp = 0; sp < 4; ++sp) {
-                    if (sp + 4 * used[sp] >= d.ntiles) continue;  // no warp left on this sub-partition
-                    if (best < 0 || load[sp] < load[best]) best = sp;
-                }
-                warp_of[i] = best + 4 * used[best];
+                for (int sp = 0; sp < 4; ++sp)
+                    if (used[sp] < 4 && (best < 0 || load[sp] < load[best])) best = sp;
+                units[i].sp = best;
                 ++used[best];
-                load[best] += cost[i];
+                load[best] += units[i].cost * 4;
             }
-            for (int i = 0; i < d.ntiles; ++i) {
-                const int wv = warp_of[i];
-                d.slot_a[wv] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].first) - h.blocks.begin());
-                d.slot_b[wv] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].second) - h.blocks.begin());
-                d.ntn[wv] = (unsigned char)cost[i];
+            auto split = [&](int u, int k, int to) {   // move k of unit u's k4-steps to a new unit on sub-partition `to`
+                int moved = 0, keep = units[u].mask;
+                for (int q = 3; q >= 0 && nq(moved) < k; --q)
+                    if ((keep >> q) & 1) { moved |= 1 << q; keep &= ~(1 << q); }
+                units[u].mask = keep;
+                load[units[u].sp] -= units[u].cost * k;
+                units.push_back({units[u].tile, units[u].cost, moved, to});
+                ++used[to];
+                load[to] += units[u].cost * k;
+            };
+            auto tile_units = [&](int tile) {
+                int c = 0;
+                for (const Unit& u : units) c += (u.tile == tile);
+                return c;
+            };
+            static const int split_max_tiles = [] {   // tuning aid: jobs with more tiles are not rebalanced
+                const char* e = std::getenv("FRK_GRAM_SPLIT_MAXTILES");
+                return e ? std::atoi(e) : NWARPS;
+            }();
+            for (;;) {
+                if (d.ntiles > split_max_tiles) break;
+                if (int(units.size()) >= NWARPS) break;
+                int hi = 0, lo = -1;
+                for (int sp = 0; sp < 4; ++sp) {
+                    if (load[sp] > load[hi]) hi = sp;
+                    if (used[sp] < 4 && (lo < 0 || load[sp] < load[lo])) lo = sp;
+                }
+                if (lo < 0 || lo == hi) break;
+                int best_u = -1, best_k = 0, best_max = load[hi];
+                for (int u = 0; u < int(units.size()); ++u) {
+                    if (units[u].sp != hi || nq(units[u].mask) < 2 || tile_units(units[u].tile) >= 4) continue;
+                    for (int k = 1; k < nq(units[u].mask); ++k) {
+                        const int nm = std::max(load[hi] - units[u].cost * k, load[lo] + units[u].cost * k);
+                        if (nm < best_max) { best_max = nm; best_u = u; best_k = k; }
+                    }
+                }
+                if (best_u < 0) break;
+                split(best_u, best_k, lo);
+            }
+            // few units: give every sub-partition a second warp to hide latency (halves on the same sub-partition)
+            while (int(units.size()) * 2 <= NWARPS) {
+                const int cnt = int(units.size());
+                bool any = false;
+                for (int u = 0; u < cnt; ++u)
+                    if (nq(units[u].mask) >= 2 && used[units[u].sp] < 4 && tile_units(units[u].tile) < 4) {
+                        split(u, nq(units[u].mask) / 2, units[u].sp);
+                        any = true;
+                    }
+                if (!any) break;
+            }
+            int next[4] = {0, 1, 2, 3};
+            d.nactive = int(units.size());
+            for (const Unit& u : units) {
+                const int wv = next[u.sp];
+                next[u.sp] += 4;
+                d.w_tile[wv] = (unsigned char)u.tile;
+                d.qmask[wv] = (unsigned char)u.mask;
+                d.ntn[wv] = (unsigned char)u.cost;
+                d.tile_w[u.tile][d.tile_nw[u.tile]++] = (unsigned char)wv;
             }
         }
         const size_t bytes = sizeof(GramJob) * dj.size() + sizeof(unsigned);
