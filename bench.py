@@ -274,6 +274,10 @@ def main_gpu(args):
     same = bool(torch.equal(torch.from_numpy(oh_np[:1000].copy()), out[:1000].cpu()))
 
     fit_block = fit_benchmarks(torch, dist, world, rank, basis, x, args) if not args.no_fit else None
+    if fit_block is not None and world == 1:   # BASELINE configs[1] and configs[2] at full size, beside the headline
+        del out
+        torch.cuda.empty_cache()
+        fit_block["other_configs"] = other_configs(torch)
 
     if rank == 0:
         flops = 2.0 * n2 * m * kstar                     # credited: projection only
@@ -320,6 +324,46 @@ def main_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(torch):
+    """BASELINE configs[1] (mrts(500 2-D knots, k=200) + predict.mrts at 1 M locations) and configs[2] (2,000 3-D
+    knots, K = 1,000, 10 M locations) at full size on one GPU: fit wall time + device-resident evaluation, CUDA events."""
+    from autofrk_b200 import mrts as G
+    from autofrk_b200._lib import FRK_OUT_BASIS
+
+    res = {}
+    for name, d, m, K, n2 in (("configs[1]", 2, 500, 200, 1_000_000), ("configs[2]", 3, 2000, 1000, 10_000_000)):
+        free, _ = torch.cuda.mem_get_info()
+        if free < (n2 * K * 8) * 1.1 + (2 << 30):
+            res[name] = {"skipped": "not enough free device memory"}
+            continue
+        knots = make_knots(m, d)
+        G.mrts(knots, K)                                           # warm-up (cuSOLVER workspaces)
+        t0 = time.perf_counter()
+        basis = G.mrts(knots, K)                                   # device fit, result on the host (the R object)
+        t_fit = time.perf_counter() - t0
+        plan = basis.plan()
+        gen = torch.Generator(device="cuda").manual_seed(77)
+        x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=gen).T
+        out = torch.empty((K, n2), dtype=torch.float64, device="cuda").T
+        plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        kstar = K - d - 1
+        res[name] = {"d": d, "knots": m, "K": K, "locations": n2, "mrts_fit_wall_ms": t_fit * 1e3, "predict_ms": best,
+                     "basis_evals_per_s": n2 * K / (best * 1e-3), "tflops_credited": 2.0 * n2 * m * kstar / best / 1e9,
+                     "kernel": plan.info}
+        del x, out, plan, basis
+        torch.cuda.empty_cache()
+    return res
 
 
 def k1_traffic(n2, m, K):
