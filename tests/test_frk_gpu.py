@@ -493,3 +493,29 @@ def test_plan_predict_frk_folded_path_edge_cases():
                 assert np.abs(se[idx] ** 2 - ref_se ** 2).max() <= 1e-10 * scale, (d, name)
                 if name == "zero":
                     assert np.all(se == 0.0)
+
+
+def test_gram_random_shapes_against_numpy():
+    """40 seeded random shapes (49 <= K <= 700, 0 <= T <= 130, ragged n, weights on and off) through the tensor-core
+    job kernel: every block pair, every trimmed edge tile and every split work unit must land in the right place."""
+    from autofrk_b200 import frk as G
+
+    rng = np.random.default_rng(2024)
+    for it in range(40):
+        K = int(rng.integers(49, 701))
+        T = int(rng.integers(0, 131))
+        n = int(rng.integers(100, 3001))
+        F = np.asfortranarray(rng.standard_normal((n, K)))
+        Z = np.asfortranarray(rng.standard_normal((n, max(T, 1))))
+        w = (rng.random(n) + 0.5) if it % 3 == 0 else None
+        Fw = F if w is None else w[:, None] * F
+        if T == 0:
+            Gm, Cm, zz = G.gram_stats(F, weights=w)
+            assert Cm is None
+        else:
+            Gm, Cm, zz = G.gram_stats(F, Z, weights=w)
+            assert relmax(Cm, Fw.T @ Z) < 1e-12, (K, T, n)
+            ref_zz = np.sum(Z * Z) if w is None else np.sum(w[:, None] * Z * Z)
+            assert abs(zz - ref_zz) / ref_zz < 1e-13, (K, T, n)
+        assert relmax(Gm, Fw.T @ F) < 1e-12, (K, T, n)
+        assert np.array_equal(Gm, Gm.T), (K, T, n)
