@@ -61,6 +61,30 @@ def test_mrtsrcpp_predict_matches_oracle(d, m, kstar, n2):
     assert np.array_equal(got2["X1"], got["X1"][:, :kstar])
 
 
+def test_mrtsrcpp_predict_random_shapes_match_oracle():
+    """24 seeded random (d, m, k*, n2): every K1 configuration and column-slice count the plan can pick, ragged row
+    and column edges, against the oracle at 1e-10 (column-max-relative)."""
+    import oracle as O
+    from autofrk_b200 import mrts as G
+
+    rs = np.random.default_rng(77)
+    for it in range(24):
+        d = int(rs.integers(1, 4))
+        m = int(rs.integers(d + 6, 420))
+        # d = 1 with many columns is intrinsically ill-conditioned (|gammas| ~ 1/rho_min, SURVEY.md 8c): keep k* small there
+        kmax = min(m - d - 1, 12 if d == 1 else 400)
+        kstar = int(rs.integers(1, kmax + 1))
+        n2 = int(rs.integers(1, 1500))
+        Xu, xd, fit, rng = make_fit(d, m, kstar, seed=1000 + it)
+        xnew = rng.random((n2, d)) * 1.2 - 0.1
+        K = kstar + d + 1
+        ref = O.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], K)["X1"]
+        got = G.mrtsrcpp_predict(Xu, xd, xnew, fit["BBBH"], fit["UZ"], fit["nconst"], K)["X1"]
+        assert got.shape == (n2, K) and np.all(got[:, kstar:] == 0.0)
+        err = colrel(got[:, :kstar], ref[:, :kstar])
+        assert err < TOL, (d, m, kstar, n2, err)
+
+
 def test_predict_mrts_basis_and_identity():
     """predict.mrts end to end + the known-answer identity predict(mrts(knot,k), knot) == mrts(knot,k)."""
     import oracle as O
