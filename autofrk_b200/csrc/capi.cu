@@ -91,16 +91,31 @@ void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, i
     for (int b = 0; b < 2; ++b)
         if (plan->dbuf[b].n < size_t(rc) * k) plan->dbuf[b].alloc(size_t(rc) * k);
     FRK_CUDA(cudaMemcpyAsync(plan->dx.p, xnew, sizeof(double) * n2 * d, cudaMemcpyHostToDevice, plan->s_comp));
-    int c = 0;
-    for (int64_t r0 = 0; r0 < n2; r0 += rc, ++c) {
+    // The device->host stream is the bottleneck (PCIe): a short first chunk gets it going after two waves of tiles
+    // instead of after a full chunk of compute.  The kernels of chunk c+1 are queued BEFORE the copy of chunk c is
+    // issued, because a copy to pageable host memory blocks the calling thread.
+    std::vector<int64_t> starts;
+    for (int64_t r0 = 0; r0 < n2;) {
+        starts.push_back(r0);
+        r0 += std::min(starts.size() == 1 ? std::min(rc, 2 * wave) : rc, n2 - r0);
+    }
+    starts.push_back(n2);
+    const int nchunk = int(starts.size()) - 1;
+    auto compute = [&](int c) {
         const int b = c & 1;
-        const int64_t rows = std::min(rc, n2 - r0);
-        if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(plan->s_comp, plan->ev_copy[b], 0));
+        const int64_t r0 = starts[c], rows = starts[c + 1] - r0;
+        if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(plan->s_comp, plan->ev_copy[b], 0));   // chunk c-2 has left the buffer
         if (mode == FRK_OUT_X1)
             frk::plan_predict_x1_dev(mp, plan->dx.p + r0, rows, n2, plan->dbuf[b].p, rc, plan->s_comp);
         else
             frk::plan_predict_basis_dev(mp, plan->dx.p + r0, rows, n2, plan->dbuf[b].p, rc, plan->s_comp);
         FRK_CUDA(cudaEventRecord(plan->ev_comp[b], plan->s_comp));
+    };
+    compute(0);
+    for (int c = 0; c < nchunk; ++c) {
+        const int b = c & 1;
+        const int64_t r0 = starts[c], rows = starts[c + 1] - r0;
+        if (c + 1 < nchunk) compute(c + 1);
         FRK_CUDA(cudaStreamWaitEvent(plan->s_copy, plan->ev_comp[b], 0));
         FRK_CUDA(cudaMemcpy2DAsync(out + r0, sizeof(double) * n2, plan->dbuf[b].p, sizeof(double) * rc,
                                    sizeof(double) * rows, size_t(k), cudaMemcpyDeviceToHost, plan->s_copy));
