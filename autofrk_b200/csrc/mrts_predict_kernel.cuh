@@ -28,7 +28,7 @@
 
 namespace frk {
 
-template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_, int AHEAD_ = 2>
+template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_, int AHEAD_ = 2, bool SPLIT_ = false>
 struct PredictCfg {
     static constexpr int D = D_, WR = WR_, WC = WC_, MT = MT_, NT = NT_, KC = KC_, NSTAGE = NSTAGE_;
     static constexpr int DP = (D == 3) ? 4 : D;   // doubles per stored coordinate tuple
@@ -44,6 +44,7 @@ struct PredictCfg {
     static constexpr int XS_DOUBLES = BM * DP;
     static constexpr int LOGTAB_DOUBLES = (D == 2) ? 2 * kLogTabSize : 0;
     static constexpr int AHEAD = AHEAD_;          // Phi is produced this many chunks ahead of its DMMAs
+    static constexpr bool PHI_SPLIT = SPLIT_;     // d = 2: overlap the halves of consecutive Phi values (see the kernel)
     static constexpr int NPB = 2 * AHEAD;         // Phi chunk buffers (>= 2 * AHEAD)
     static constexpr int MIN_CHUNKS = (2 * AHEAD > 4) ? 2 * AHEAD : 4;  // the plan pads the knot list to at least this many chunks
     static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + NPB * PHI_DOUBLES * 8 + 2 * XS_DOUBLES * 8 +
@@ -115,6 +116,35 @@ __device__ __forceinline__ double phi2_table(double x, const double2* __restrict
     return (x > 0.0) ? x * L : 0.0;
 }
 
+// phi2_table cut in two so that a thread can overlap the halves of two consecutive values (the first half of the
+// next value with the second half of the current one): the 10-deep dependent FP64 chain becomes two independent
+// ~5-deep chains in one basic block.  Same operations in the same order: bitwise identical to phi2_table.
+struct Phi2Half {
+    double r, x, lcc;
+    int e;
+};
+__device__ __forceinline__ Phi2Half phi2_table_head(double x, const double2* __restrict__ tab) {
+    const long long bits = __double_as_longlong(x);
+    const int hi = int(bits >> 32);
+    const double2 tc = tab[(hi >> (20 - kLogTabBits)) & (kLogTabSize - 1)];
+    const double m = __longlong_as_double((bits & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
+    Phi2Half h;
+    h.r = fma(m, tc.x, -1.0);
+    h.x = x;
+    h.lcc = tc.y;
+    h.e = (hi >> 20) - 1023;
+    return h;
+}
+__device__ __forceinline__ double phi2_table_tail(const Phi2Half& h) {
+    constexpr double c = 0x1.45f306dc9c883p-6;  // 1/(16 pi)
+    double p = fma(-0.25 * c, h.r, c / 3.0);
+    p = fma(p, h.r, -0.5 * c);
+    p = fma(p, h.r, c);
+    const double s = fma(h.r, p, h.lcc);
+    const double L = fma(double(h.e), 0x1.c3dc98f7e969cp-7, s);  // ln2 / (16 pi)
+    return (h.x > 0.0) ? h.x * L : 0.0;
+}
+
 // Branch-free FP64 sqrt of x >= 0: MUFU seed (rsqrt.approx.f64, ~2^-21), two Newton steps on 1/sqrt, one
 // correction of x*y.  Correctly rounded on 3e7 random inputs with a 2^-21-perturbed seed; keeps
 // the d = 3 kernel in the DMMA basic block (libm sqrt carries a slow-path branch).
@@ -164,6 +194,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     constexpr int PHI_Q = 0;  // k4-group after which the Phi arithmetic is placed in the source (ptxas spreads it anyway)
 #endif
     constexpr bool PREFETCH = (VPT <= 2);     // knots one iteration early in registers (if they are affordable)
+    // d = 2, one Phi value per thread and chunk: halves of consecutive values overlapped (phi2_table_head / _tail);
+    // with two values per thread the extra state spills.  Opt-in per configuration: whether ptxas turns the two
+    // shorter chains into a better schedule is measured, not assumed (BN 384: +1.6%, BN 512: -2.5%).
+    constexpr bool SPLIT = C::PHI_SPLIT && (VPT == 1) && (D == 2);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const stage0 = reinterpret_cast<double*>(smem_raw);
@@ -264,8 +298,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
         __syncwarp();
         if (lane == 0) mbar_arrive(&phi_full[j]);
     }
+    [[maybe_unused]] Phi2Half half[SPLIT ? VPT : 1];   // SPLIT: first half of Phi(it + AHEAD), computed during iteration it - 1
+    if constexpr (SPLIT) {            // first half of Phi(AHEAD) (tile 0: nchunks >= 2 AHEAD), knots of chunk AHEAD + 1
+        knots_load(AHEAD, pu);
+        rows_load(0);
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const double dx = px[i][0] - pu[i][0], dy = px[i][1] - pu[i][1];
+            half[i] = phi2_table_head(fma(dx, dx, dy * dy), logtab);
+        }
+    }
     if constexpr (PREFETCH) {
-        const double* k0 = a.knots + size_t(AHEAD % nchunks) * (KC * DP);
+        const double* k0 = a.knots + size_t((AHEAD + (SPLIT ? 1 : 0)) % nchunks) * (KC * DP);
 #pragma unroll
         for (int i = 0; i < VPT; ++i)
 #pragma unroll
@@ -324,7 +368,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
             // (2) inputs of the Phi chunk produced in this iteration (rows from shared, knots prefetched)
             const bool more = (left > AHEAD);
             // without prefetch: knots of the Phi chunk produced now; with: those of the next iteration's
-            const int cknot = PREFETCH ? ((cphi + 1 == nchunks) ? 0 : cphi + 1) : cphi;
+            // SPLIT: the registers hold the knots of chunk cphi + 1 (its first half runs now), loads fetch cphi + 2
+            const int cknot = !PREFETCH ? cphi : (cphi + (SPLIT ? 2 : 1) >= nchunks) ? cphi + (SPLIT ? 2 : 1) - nchunks
+                                                                                  : cphi + (SPLIT ? 2 : 1);
             const double* knots_c = a.knots + size_t(cknot) * (KC * DP);
             double pu_now[PREFETCH ? VPT : 1][3];
             if constexpr (PREFETCH) {
@@ -336,7 +382,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                         pun[i][cc] = __ldg(knots_c + phi_kk[i] * DP + cc);
                     }
             }
-            const double* xs_c = xs + ((c + AHEAD >= nchunks) ? (xb ^ 1) : xb) * C::XS_DOUBLES;
+            const double* xs_c = xs + ((c + AHEAD + (SPLIT ? 1 : 0) >= nchunks) ? (xb ^ 1) : xb) * C::XS_DOUBLES;
             // (3) W of this chunk landed
             if (!okw) mbar_wait(&w_full[s], wpar);
 
@@ -370,7 +416,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                             if constexpr (PREFETCH) u1[cc] = pu_now[i][cc];
                             else u1[cc] = __ldg(knots_c + phi_kk[i] * DP + cc);
                         }
-                        val[i] = tps_phi_fast<D>(x1, u1, logtab);
+                        if constexpr (SPLIT) {
+                            val[i] = phi2_table_tail(half[i]);               // Phi(it + AHEAD), started last iteration
+                            const double dx = x1[0] - u1[0], dy = x1[1] - u1[1];
+                            half[i] = phi2_table_head(fma(dx, dx, dy * dy), logtab);   // Phi(it + AHEAD + 1)
+                        } else {
+                            val[i] = tps_phi_fast<D>(x1, u1, logtab);
+                        }
                     }
                 }
                 if (q == KQ - 1) {  // probe the next iteration's barriers while the last DMMAs drain
@@ -471,12 +523,14 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>(),  /* BM  96, BN 200, 4 Phi/thread, 15 warps */        \
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
     predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>(), /* BM  64, BN 320, Phi 3 ahead */                  \
-    predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3>>(), /* BM  32, BN 384, 1 Phi/thread, Phi 3 ahead */  \
+    predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, true>>(), /* BM 32, BN 384, 1 Phi/thread, Phi 3 ahead, split Phi */ \
     predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>()  /* BM  32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead */ \
     FRK_PREDICT_EXTRA_CONFIGS(D)
 #ifdef FRK_EXPERIMENTAL_CONFIGS   // Phi ring depth study (tools/k1_cfg_probe.py with FRK_K1_CONFIG)
 #define FRK_PREDICT_EXTRA_CONFIGS(D)                                                                       \
     , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 12: BN 512, 3 stages, AHEAD 2 (v6) */         \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3, true>>() /* BN 512 with split Phi */                \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, false>>() /* BN 384 without split Phi */            \
     , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 2>>() /* 13: BN 512, 2 stages, AHEAD 2 */              \
     , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 4>>() /* 14: BN 512, 2 stages, AHEAD 4 */              \
     , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4, 2>>() /* 15: BN 384, 4 stages, AHEAD 2 (v6) */         \
