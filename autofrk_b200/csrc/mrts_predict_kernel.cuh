@@ -28,7 +28,8 @@
 
 namespace frk {
 
-template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_, int AHEAD_ = 2, bool SPLIT_ = false>
+template <int D_, int WR_, int WC_, int MT_, int NT_, int KC_, int NSTAGE_, int AHEAD_ = 2, bool SPLIT_ = false,
+          bool KSM_ = false>
 struct PredictCfg {
     static constexpr int D = D_, WR = WR_, WC = WC_, MT = MT_, NT = NT_, KC = KC_, NSTAGE = NSTAGE_;
     static constexpr int DP = (D == 3) ? 4 : D;   // doubles per stored coordinate tuple
@@ -45,6 +46,8 @@ struct PredictCfg {
     static constexpr int LOGTAB_DOUBLES = (D == 2) ? 2 * kLogTabSize : 0;
     static constexpr int AHEAD = AHEAD_;          // Phi is produced this many chunks ahead of its DMMAs
     static constexpr bool PHI_SPLIT = SPLIT_;     // d = 2: overlap the halves of consecutive Phi values (see the kernel)
+    static constexpr bool KNOTS_SMEM = KSM_;      // knot coordinates staged in shared memory behind SMEM_BYTES (if they fit)
+    using Fallback = PredictCfg<D_, WR_, WC_, MT_, NT_, KC_, NSTAGE_, AHEAD_, false, false>;  // when they do not
     static constexpr int NPB = 2 * AHEAD;         // Phi chunk buffers (>= 2 * AHEAD)
     static constexpr int MIN_CHUNKS = (2 * AHEAD > 4) ? 2 * AHEAD : 4;  // the plan pads the knot list to at least this many chunks
     static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + NPB * PHI_DOUBLES * 8 + 2 * XS_DOUBLES * 8 +
@@ -193,11 +196,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
 #else
     constexpr int PHI_Q = 0;  // k4-group after which the Phi arithmetic is placed in the source (ptxas spreads it anyway)
 #endif
-    constexpr bool PREFETCH = (VPT <= 2);     // knots one iteration early in registers (if they are affordable)
+    constexpr bool KSM = C::KNOTS_SMEM;       // knots in shared memory: no global loads in the loop, no prefetch registers
+    constexpr bool PREFETCH = (VPT <= 2) && !KSM;  // knots one iteration early in registers (if they are affordable)
     // d = 2, one Phi value per thread and chunk: halves of consecutive values overlapped (phi2_table_head / _tail);
     // with two values per thread the extra state spills.  Opt-in per configuration: whether ptxas turns the two
     // shorter chains into a better schedule is measured, not assumed (BN 384: +1.6%, BN 512: -2.5%).
     constexpr bool SPLIT = C::PHI_SPLIT && (VPT == 1) && (D == 2);
+    constexpr size_t KNOTS_OFFSET = (C::SMEM_BYTES + 15) / 16 * 16;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* const stage0 = reinterpret_cast<double*>(smem_raw);
@@ -208,6 +213,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     uint64_t* const phi_full = w_full + NSTAGE;    // all warps stored their part of a Phi chunk
     uint32_t* const w_done = reinterpret_cast<uint32_t*>(phi_full + NPB);  // warps done with a W stage
     const double2* const logtab = reinterpret_cast<const double2*>(logtab_d);
+    double* const knots_s = reinterpret_cast<double*>(smem_raw + KNOTS_OFFSET);   // KSM only
+    const double* const kn = KSM ? knots_s : a.knots;
+    auto ldk = [&](const double* p) { return KSM ? *p : __ldg(p); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -232,6 +240,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                 tma_bulk_g2s(stage0 + size_t(s) * C::STAGE_DOUBLES,
                              a.wpack + size_t(s % nchunks) * C::STAGE_DOUBLES, C::STAGE_BYTES, &w_full[s]);
             }
+    }
+    if constexpr (KSM) {
+        const int nk = a.nchunks * KC * DP;
+        for (int i = tid; i < nk; i += NTHREADS) knots_s[i] = __ldg(a.knots + i);
     }
     if constexpr (D == 2) {
         for (int i = tid; i < kLogTabSize; i += NTHREADS) {
@@ -262,11 +274,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
     }
     double px[VPT][3], pu[VPT][3];  // coordinates of the pending Phi evaluations
     auto knots_load = [&](int chunk, double (&dst)[VPT][3]) {
-        const double* knots = a.knots + size_t(chunk) * (KC * DP);
+        const double* knots = kn + size_t(chunk) * (KC * DP);
 #pragma unroll
         for (int i = 0; i < VPT; ++i)
 #pragma unroll
-            for (int c = 0; c < D; ++c) dst[i][c] = __ldg(knots + phi_kk[i] * DP + c);
+            for (int c = 0; c < D; ++c) dst[i][c] = ldk(knots + phi_kk[i] * DP + c);
     };
     auto rows_load = [&](int xbuf) {
         const double* xsb = xs + xbuf * C::XS_DOUBLES;
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
         }
     }
     if constexpr (PREFETCH) {
-        const double* k0 = a.knots + size_t((AHEAD + (SPLIT ? 1 : 0)) % nchunks) * (KC * DP);
+        const double* k0 = kn + size_t((AHEAD + (SPLIT ? 1 : 0)) % nchunks) * (KC * DP);
 #pragma unroll
         for (int i = 0; i < VPT; ++i)
 #pragma unroll
@@ -369,9 +381,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
             const bool more = (left > AHEAD);
             // without prefetch: knots of the Phi chunk produced now; with: those of the next iteration's
             // SPLIT: the registers hold the knots of chunk cphi + 1 (its first half runs now), loads fetch cphi + 2
-            const int cknot = !PREFETCH ? cphi : (cphi + (SPLIT ? 2 : 1) >= nchunks) ? cphi + (SPLIT ? 2 : 1) - nchunks
-                                                                                  : cphi + (SPLIT ? 2 : 1);
-            const double* knots_c = a.knots + size_t(cknot) * (KC * DP);
+            constexpr int KOFF = (SPLIT ? 1 : 0) + (PREFETCH ? 1 : 0);   // chunk whose knots are read in this iteration
+            const int cknot = (cphi + KOFF >= nchunks) ? cphi + KOFF - nchunks : cphi + KOFF;
+            const double* knots_c = kn + size_t(cknot) * (KC * DP);
             double pu_now[PREFETCH ? VPT : 1][3];
             if constexpr (PREFETCH) {
 #pragma unroll
@@ -414,7 +426,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) mrts_predict_kernel(const Pred
                         for (int cc = 0; cc < D; ++cc) {
                             x1[cc] = xs_c[phi_row[i] * DP + cc];
                             if constexpr (PREFETCH) u1[cc] = pu_now[i][cc];
-                            else u1[cc] = __ldg(knots_c + phi_kk[i] * DP + cc);
+                            else u1[cc] = ldk(knots_c + phi_kk[i] * DP + cc);
                         }
                         if constexpr (SPLIT) {
                             val[i] = phi2_table_tail(half[i]);               // Phi(it + AHEAD), started last iteration
@@ -490,14 +502,30 @@ inline size_t predict_smem_pad(size_t base) {
 #else
 inline size_t predict_smem_pad(size_t) { return 0; }
 #endif
+constexpr size_t kMaxDynSmem = 227 * 1024;
+template <class C>
+size_t predict_knots_smem_total(const PredictArgs& a) {   // dynamic shared memory with the knots staged behind the rest
+    return (C::SMEM_BYTES + 15) / 16 * 16 + size_t(a.nchunks) * C::KC * C::DP * sizeof(double);
+}
 template <class C>
 void predict_prepare() {
-    FRK_CUDA(cudaFuncSetAttribute(mrts_predict_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES))));
+    if constexpr (C::KNOTS_SMEM) {
+        FRK_CUDA(cudaFuncSetAttribute(mrts_predict_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxDynSmem)));
+        predict_prepare<typename C::Fallback>();
+    } else {
+        FRK_CUDA(cudaFuncSetAttribute(mrts_predict_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES))));
+    }
 }
 template <class C>
 void predict_launch(const PredictArgs& a, int grid, cudaStream_t st) {
-    mrts_predict_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES), st>>>(a);
+    if constexpr (C::KNOTS_SMEM) {
+        const size_t total = predict_knots_smem_total<C>(a);
+        if (total <= kMaxDynSmem) mrts_predict_kernel<C><<<grid, C::NTHREADS, total, st>>>(a);
+        else predict_launch<typename C::Fallback>(a, grid, st);   // too many knots for shared memory
+    } else {
+        mrts_predict_kernel<C><<<grid, C::NTHREADS, C::SMEM_BYTES + predict_smem_pad(C::SMEM_BYTES), st>>>(a);
+    }
 }
 template <class C>
 constexpr PredictKernelInfo predict_info() {
@@ -521,22 +549,21 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 4, 4, 4, 4, 16, 4>>(),  /* BM 128, BN 128 */                                \
     predict_info<PredictCfg<D, 2, 8, 4, 3, 16, 4>>(),  /* BM  64, BN 192, 2 Phi/thread */                  \
     predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>(),  /* BM  96, BN 200, 4 Phi/thread, 15 warps */        \
-    predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4>>(),  /* BM  64, BN 256 */                                \
-    predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>(), /* BM  64, BN 320, Phi 3 ahead */                  \
+    predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4, 2, false, true>>(), /* BM  64, BN 256, knots in smem */   \
+    predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3, false, true>>(), /* BM 64, BN 320, Phi 3 ahead, knots in smem */ \
     predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, true>>(), /* BM 32, BN 384, 1 Phi/thread, Phi 3 ahead, split Phi */ \
-    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>()  /* BM  32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead */ \
+    predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3, false, true>>() /* BM 32, BN 512, 1 Phi/thread, 2 x 64 KB stages, Phi 3 ahead, knots in smem */ \
     FRK_PREDICT_EXTRA_CONFIGS(D)
 #ifdef FRK_EXPERIMENTAL_CONFIGS   // Phi ring depth study (tools/k1_cfg_probe.py with FRK_K1_CONFIG)
 #define FRK_PREDICT_EXTRA_CONFIGS(D)                                                                       \
-    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 12: BN 512, 3 stages, AHEAD 2 (v6) */         \
-    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3, true>>() /* BN 512 with split Phi */                \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, false>>() /* BN 384 without split Phi */            \
-    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 2>>() /* 13: BN 512, 2 stages, AHEAD 2 */              \
-    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 4>>() /* 14: BN 512, 2 stages, AHEAD 4 */              \
-    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 4, 2>>() /* 15: BN 384, 4 stages, AHEAD 2 (v6) */         \
-    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 4, 2>>()  /* 16: BN 320, 4 stages, AHEAD 2 (v6) */         \
-    , predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()     /* 17: BN 512, 8 fat warps (32 x 64 tiles) */     \
-    , predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()     /* 18: BN 200, 20 thin warps, 2 Phi/thread */
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3>>()  /* 12: BN 512, knots from global memory (v7) */  \
+    , predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3>>()   /* 13: BN 320, knots from global memory */      \
+    , predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4, 2>>()   /* 14: BN 256, knots from global memory */      \
+    , predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, false, true>>() /* 15: BN 384, knots in smem, single Phi chain */ \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 16: BN 512, 3 stages, AHEAD 2 (v6) */         \
+    , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3, true>>() /* 17: BN 512 with split Phi */            \
+    , predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()     /* 18: BN 512, 8 fat warps (32 x 64 tiles) */     \
+    , predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()     /* 19: BN 200, 20 thin warps, 2 Phi/thread */
 #else
 #define FRK_PREDICT_EXTRA_CONFIGS(D)
 #endif
