@@ -116,7 +116,7 @@ __device__ __forceinline__ double phi2_table(double x, const double2* __restrict
     p = fma(p, r, c);
     const double s = fma(r, p, tc.y);
     const double L = fma(ef, 0x1.c3dc98f7e969cp-7, s);  // ln2 / (16 pi) = 0.013789725009540725
-    return (x > 0.0) ? x * L : 0.0;
+    return (bits > 0) ? x * L : 0.0;   // x = r^2 >= 0: an integer test on the bits keeps the comparison off the FP64 pipe
 }
 
 // phi2_table cut in two so that a thread can overlap the halves of two consecutive values (the first half of the
@@ -145,7 +145,7 @@ __device__ __forceinline__ double phi2_table_tail(const Phi2Half& h) {
     p = fma(p, h.r, c);
     const double s = fma(h.r, p, h.lcc);
     const double L = fma(double(h.e), 0x1.c3dc98f7e969cp-7, s);  // ln2 / (16 pi)
-    return (h.x > 0.0) ? h.x * L : 0.0;
+    return (__double_as_longlong(h.x) > 0) ? h.x * L : 0.0;
 }
 
 // Branch-free FP64 sqrt of x >= 0: MUFU seed (rsqrt.approx.f64, ~2^-21), two Newton steps on 1/sqrt, one
