@@ -99,7 +99,7 @@ __device__ __forceinline__ double tps_phi(const double* __restrict__ x, const do
 // Branch-free d = 2 kernel value phi(x) = x log(x) / (16 pi) for x = r^2 >= 0 (Tang-style, 1024-entry table
 // in shared memory): x = 2^e m, m in [1,2); j = top 10 mantissa bits, r = m*rc_j - 1 (one FMA, |r| <= 2^-11);
 //   log(x)/(16 pi) = e ln2/(16 pi) + lcc_j + c (r - r^2/2 + r^3/3 - r^4/4),   c = 1/(16 pi)   (|c r^5/5| < 2e-19)
-// 13 FP64-pipe instructions per pair (libm log alone is ~50 pipe slots); absolute error 5.1e-18 on (0,2) against
+// 11 FP64-pipe instructions per pair, r^2 included (libm log alone is ~50 pipe slots); absolute error 5.1e-18 on (0,2) against
 // 6.6e-18 for x*log(x)/(16 pi) with libm (tools/gen_log_table.py).  e*ln2 needs no hi/lo split: its
 // rounding error is multiplied by x = 2^e m, i.e. it is <= 1 ulp of phi.  x == 0 is masked; subnormal x gives a
 // value <= 1e-305 in magnitude; inf / nan propagate through the final multiplication by x.
