@@ -129,3 +129,22 @@ def test_getASCeigens():
     V = got["vector"]
     assert np.max(np.abs(V.T @ V - np.eye(120))) < 1e-12
     assert np.max(np.abs(A @ V - V * got["value"])) / got["value"].max() < 1e-12
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_rigid_motion_invariance_on_the_gpu(d):
+    """size-independent property (no oracle): rotating + translating knots and 50,000 locations together leaves the
+    non-polynomial basis columns unchanged up to sign (distance-only kernel, affine part centred out)."""
+    from autofrk_b200 import mrts as G
+
+    rng = np.random.default_rng(43)
+    m, K, n2 = 300, 60, 50_000
+    Xu = rng.random((m, d))
+    x = rng.random((n2, d))
+    Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    shift = rng.standard_normal(d)
+    A = G.predict_mrts(G.mrts(Xu, K), x)[:, d + 1:]
+    B = G.predict_mrts(G.mrts(Xu @ Q + shift, K), x @ Q + shift)[:, d + 1:]
+    s = np.sign(np.sum(A * B, axis=0))
+    err = np.max(np.max(np.abs(A * s - B), axis=0) / np.max(np.abs(B), axis=0))
+    assert err < 1e-7, err
