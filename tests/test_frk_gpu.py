@@ -519,3 +519,26 @@ def test_gram_random_shapes_against_numpy():
             assert abs(zz - ref_zz) / ref_zz < 1e-13, (K, T, n)
         assert relmax(Gm, Fw.T @ F) < 1e-12, (K, T, n)
         assert np.array_equal(Gm, Gm.T), (K, T, n)
+
+
+def test_cMLEimat_scale_equivariance():
+    """oracle-free property of the closed-form MLE: Data -> a * Data scales v and M by a^2, w by a, V by a^2 and shifts
+    negloglik by n T log(a^2); the basis may be rescaled column-wise (F -> F diag(c)) with M -> C^-1 M C^-1, w -> C^-1 w
+    and an unchanged likelihood."""
+    from autofrk_b200 import frk as G
+
+    n, K, T = 6000, 30, 4
+    F, Z = _data(n, K, T, seed=99)
+    base = G.cMLEimat(F, Z, 0.0, wSave=True)
+    a = 3.7
+    sc = G.cMLEimat(F, a * Z, 0.0, wSave=True)
+    assert abs(sc["v"] - a * a * base["v"]) <= 1e-10 * sc["v"]
+    assert relmax(sc["M"], a * a * base["M"]) < 1e-10 and relmax(sc["V"], a * a * base["V"]) < 1e-9
+    assert relmax(sc["w"], a * base["w"]) < 1e-10
+    assert abs(sc["negloglik"] - (base["negloglik"] + n * T * np.log(a * a))) <= 1e-10 * abs(sc["negloglik"])
+    c = np.random.default_rng(5).random(K) + 0.5
+    rs = G.cMLEimat(np.asfortranarray(F * c), Z, 0.0, wSave=True)
+    assert abs(rs["v"] - base["v"]) <= 1e-10 * base["v"]
+    assert abs(rs["negloglik"] - base["negloglik"]) <= 1e-10 * abs(base["negloglik"])
+    assert relmax(rs["M"], base["M"] / np.outer(c, c)) < 1e-9
+    assert relmax(rs["w"], base["w"] / c[:, None]) < 1e-9
