@@ -53,7 +53,7 @@ struct GramJob {
     int slot_block[MAXSLOTS];
     // per warp: the tile it works on, the k4-steps of every stage it takes (bit q of qmask; 0 = idle warp),
     // and how many 8-column groups of block b hold real columns (1..4)
-    unsigned char w_tile[NWARPS], qmask[NWARPS], ntn[NWARPS];
+    unsigned char w_tile[NWARPS], qmask[NWARPS], ntn[NWARPS];   // ntn = 5: full diagonal block, upper 8 x 8 sub-tiles only
     // per tile: its two staged blocks and the warps whose partial sums make it up
     unsigned char slot_a[NWARPS], slot_b[NWARPS], tile_nw[NWARPS], tile_w[NWARPS][4];
 };
@@ -167,8 +167,9 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             if (WEIGHTED && nsteps > 0) load_w(0);
             double wcur[4];
             // this warp's k4-steps of one stage on the first NTN 8-column groups of block b
-            auto ksteps = [&](const unsigned char* As, auto ntn_c) {
+            auto ksteps = [&](const unsigned char* As, auto ntn_c, auto diag_c) {
                 constexpr int NTN = decltype(ntn_c)::value;
+                constexpr bool DIAG = decltype(diag_c)::value;   // diagonal block of G: 8 x 8 sub-tiles with nt >= mt only
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (!((qmask >> q) & 1)) continue;   // warp-uniform
@@ -184,7 +185,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < NTN; ++nt) dmma_nv(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                        for (int nt = DIAG ? mt : 0; nt < NTN; ++nt) dmma_nv(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
                 }
             };
             bool ok = false;
@@ -199,10 +200,11 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 for (int q = 0; q < 4; ++q) wcur[q] = wq[q];
                 if (WEIGHTED && step + 1 < nsteps) load_w(step + 1);
                 switch (ntn) {  // warp-uniform: real branches, never predicated-off DMMAs
-                    case 1: ksteps(As, std::integral_constant<int, 1>{}); break;
-                    case 2: ksteps(As, std::integral_constant<int, 2>{}); break;
-                    case 3: ksteps(As, std::integral_constant<int, 3>{}); break;
-                    default: ksteps(As, std::integral_constant<int, 4>{}); break;
+                    case 1: ksteps(As, std::integral_constant<int, 1>{}, std::false_type{}); break;
+                    case 2: ksteps(As, std::integral_constant<int, 2>{}, std::false_type{}); break;
+                    case 3: ksteps(As, std::integral_constant<int, 3>{}, std::false_type{}); break;
+                    case 5: ksteps(As, std::integral_constant<int, 4>{}, std::true_type{}); break;   // diagonal block
+                    default: ksteps(As, std::integral_constant<int, 4>{}, std::false_type{}); break;
                 }
                 if (step + 1 < nsteps) ok = mbar_test_wait(&full[lsn], lparn);
                 __syncwarp();
@@ -430,13 +432,15 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
             // the least loaded sub-partition; then, while a warp is free, part of a unit moves from the busiest
             // sub-partition to the idlest one (a tile split over warps is added up by the reduction kernel), so
             // e.g. the 10 tiles of a diagonal macro tile cost 2.5 tile-times per sub-partition instead of 3,3,2,2.
-            struct Unit { int tile, cost, mask, sp; };
+            struct Unit { int tile, cost, mask, sp, ntn; };   // cost in 8 x 8 sub-tiles per k4-step (16 = full tile)
             std::vector<Unit> units;
             std::vector<int> order(d.ntiles);
             for (int i = 0; i < d.ntiles; ++i) {
                 const int bb = h.tiles[i].second;
                 const int valid = std::min(CB, bb < a.kb ? K - bb * CB : T - (bb - a.kb) * CB);
-                units.push_back({i, (valid + 7) / 8, 0xF, -1});
+                const int ntn = (valid + 7) / 8;
+                const bool diag = (h.tiles[i].first == bb) && ntn == 4;   // upper-triangular sub-tiles only (10 of 16)
+                units.push_back({i, diag ? 10 : 4 * ntn, 0xF, -1, diag ? 5 : ntn});
                 order[i] = i;
                 d.slot_a[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].first) - h.blocks.begin());
                 d.slot_b[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].second) - h.blocks.begin());
@@ -458,7 +462,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
                     if ((keep >> q) & 1) { moved |= 1 << q; keep &= ~(1 << q); }
                 units[u].mask = keep;
                 load[units[u].sp] -= units[u].cost * k;
-                units.push_back({units[u].tile, units[u].cost, moved, to});
+                units.push_back({units[u].tile, units[u].cost, moved, to, units[u].ntn});
                 ++used[to];
                 load[to] += units[u].cost * k;
             };
@@ -509,7 +513,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
                 next[u.sp] += 4;
                 d.w_tile[wv] = (unsigned char)u.tile;
                 d.qmask[wv] = (unsigned char)u.mask;
-                d.ntn[wv] = (unsigned char)u.cost;
+                d.ntn[wv] = (unsigned char)u.ntn;
                 d.tile_w[u.tile][d.tile_nw[u.tile]++] = (unsigned char)wv;
             }
         }
