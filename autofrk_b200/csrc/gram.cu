@@ -192,15 +192,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gram_kernel(const GramArgs a) {
             }
 }
 
-// sum of squares of Z (n x T, ld ldz): fixed grid, per-block partials, summed later in a fixed order
+// sum of squares of Z (n x T, ld ldz): fixed grid (gx blocks per column group, grid.y column groups), per-block
+// partials summed later in a fixed order.  Rows are the fast index: coalesced loads, no integer division per element.
 __global__ void sumsq_kernel(const double* __restrict__ Z, int64_t ldz, int64_t n, int T, const double* __restrict__ w,
                              double* __restrict__ part) {
     double s = 0.0;
-    const int64_t total = n * int64_t(T);
-    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t c = idx / n, i = idx % n;
-        const double z = Z[i + c * ldz];
-        s = fma(w ? z * w[i] : z, z, s);
+    for (int c = blockIdx.y; c < T; c += gridDim.y) {
+        const double* col = Z + int64_t(c) * ldz;
+        for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+            const double z = col[i];
+            s = fma(w ? z * w[i] : z, z, s);
+        }
     }
     __shared__ double sh[256];
     sh[threadIdx.x] = s;
@@ -209,7 +211,7 @@ __global__ void sumsq_kernel(const double* __restrict__ Z, int64_t ldz, int64_t 
         if (threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
         __syncthreads();
     }
-    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+    if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
 }
 
 // add the row-split partials in split order and scatter into packed = [G (K x K) | C (K x T) | zz]
@@ -273,7 +275,9 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     const int nzz = 512;
     if (ws.zzpart.n < size_t(nzz)) ws.zzpart.alloc(nzz);
     if (T > 0) {
-        sumsq_kernel<<<nzz, 256, 0, st>>>(dZ, ldz, n, T, dw, ws.zzpart.p);
+        const int gy = std::min(T, 32), gx = nzz / gy;   // gx * gy <= nzz partials; the rest stay zero
+        if (gx * gy < nzz) FRK_CUDA(cudaMemsetAsync(ws.zzpart.p + gx * gy, 0, sizeof(double) * (nzz - gx * gy), st));
+        sumsq_kernel<<<dim3(unsigned(gx), unsigned(gy)), 256, 0, st>>>(dZ, ldz, n, T, dw, ws.zzpart.p);
     } else {
         FRK_CUDA(cudaMemsetAsync(ws.zzpart.p, 0, sizeof(double) * nzz, st));
     }
