@@ -37,15 +37,19 @@ namespace frk {
 namespace {
 
 constexpr int CB = 32;                            // columns per block = warp tile edge
-constexpr int KR = 16;                            // rows per pipeline stage
-constexpr int NST = 6;
+// Rows per pipeline stage: 16 (six 32 KB stages) for shapes whose jobs stage many column blocks, 32 (three 64 KB
+// stages, half the per-stage synchronisation) when all column blocks fit one job's slots (K + T small): measured
+// n = 5e6: K = 64, T = 4 1.66 -> 1.35 ms and K = 200, T = 20 9.07 -> 8.72 ms with 32, but K = 500, T = 100 56.9 -> 58.8 ms.
+constexpr int BOXR = 16;                          // rows per TMA box: 16 doubles = the 128-byte swizzle span
+__host__ __device__ constexpr int stages_for(int kr) { return kr == 16 ? 6 : 3; }
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXSLOTS = 8;
-constexpr int SLOT_BYTES = CB * KR * 8;           // 4 KB, 1024-byte aligned (swizzle atom)
-constexpr int STAGE_BYTES = MAXSLOTS * SLOT_BYTES;
+constexpr int HALF_BYTES = CB * BOXR * 8;         // one TMA box: 4 KB, 1024-byte aligned (swizzle atom)
+constexpr size_t smem_bytes_for(int kr) {
+    return size_t(stages_for(kr)) * MAXSLOTS * (CB * kr * 8) + 1024 /* alignment slack */ + 256;
+}
 constexpr int TILE_DOUBLES = CB * CB;
-constexpr size_t SMEM_BYTES = size_t(NST) * STAGE_BYTES + 1024 /* alignment slack */ + 256;
 
 // one job: column blocks to stage (F blocks are < kb, Z blocks follow) and the block pairs computed from them
 struct GramJob {
@@ -60,6 +64,7 @@ struct GramJob {
 
 struct GramTmaArgs {
     int K, T, kb;            // kb = number of 32-column blocks of F
+    int kr;                  // rows per stage the job table was built for (16 or 32)
     int64_t n;
     const double* w;
     int njobs, nsplit, nitems;
@@ -81,9 +86,13 @@ __device__ __forceinline__ void dmma_nv(double& c0, double& c1, double a, double
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <bool WEIGHTED>
+template <bool WEIGHTED, int KR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmZ, const GramTmaArgs a) {
+    constexpr int KQ = KR / 4;                        // k4-steps per stage
+    constexpr int NST = stages_for(KR);
+    constexpr int SLOT_BYTES = CB * KR * 8;           // KR / 16 boxes per staged column block
+    constexpr int STAGE_BYTES = MAXSLOTS * SLOT_BYTES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* const base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* const full = reinterpret_cast<uint64_t*>(base + size_t(NST) * STAGE_BYTES);
@@ -127,9 +136,10 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         const int sb = __ldg(&job->slot_b[tile]);
         const int ntn = __ldg(&job->ntn[warp]);
         // the slot this lane copies when its warp re-arms a stage
-        const int my_block = (lane < nslots) ? __ldg(&job->slot_block[lane]) : 0;
-        const CUtensorMap* const my_tm = (my_block < a.kb) ? &tmF : &tmZ;
-        const int my_col = ((my_block < a.kb) ? my_block : my_block - a.kb) * CB;
+        const int my_slot = lane / (KR / BOXR);
+        const int my_block = (my_slot < nslots) ? __ldg(&job->slot_block[my_slot]) : 0;
+        const CUtensorMap* const sl_tm = (my_block < a.kb) ? &tmF : &tmZ;
+        const int sl_col = ((my_block < a.kb) ? my_block : my_block - a.kb) * CB;
         const uint32_t stage_tx = uint32_t(nslots) * SLOT_BYTES;
 
         const int64_t r_begin = (split < a.nsplit_big) ? int64_t(split) * a.rows_big
@@ -142,7 +152,10 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             const int r0 = int(r_begin + int64_t(step) * KR);
             if (lane == 0) mbar_expect_tx(&full[stage], stage_tx);
             __syncwarp();
-            if (lane < nslots) tma_load_2d(As + lane * SLOT_BYTES, my_tm, r0, my_col, &full[stage]);
+            constexpr int BOXES = KR / BOXR;   // lane -> (slot, 16-row box of the slot)
+            const int sl = lane / BOXES, bx = lane % BOXES;
+            if (sl < nslots)
+                tma_load_2d(As + sl * SLOT_BYTES + bx * HALF_BYTES, sl_tm, r0 + bx * BOXR, sl_col, &full[stage]);
         };
         if (warp == 0)
             for (int i = 0; i < NST && i < nsteps; ++i) issue((s + i) % NST, i);
@@ -156,28 +169,30 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         if (active) {
             const int a_line = sa * SLOT_BYTES + g * 128;
             const int b_line = sb * SLOT_BYTES + g * 128;
-            double wq[4] = {1.0, 1.0, 1.0, 1.0};
+            double wq[KQ];
+#pragma unroll
+            for (int q = 0; q < KQ; ++q) wq[q] = 1.0;
             auto load_w = [&](int step) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int64_t r = r_begin + int64_t(step) * KR + 2 * q + (t & 1) + 8 * (t >> 1);
+                for (int q = 0; q < KQ; ++q) {
+                    const int64_t r = r_begin + int64_t(step) * KR + BOXR * (q >> 2) + 2 * (q & 3) + (t & 1) + 8 * (t >> 1);
                     wq[q] = (r < r_end) ? __ldg(a.w + r) : 0.0;
                 }
             };
             if (WEIGHTED && nsteps > 0) load_w(0);
-            double wcur[4];
+            double wcur[KQ];
             // this warp's k4-steps of one stage on the first NTN 8-column groups of block b
             auto ksteps = [&](const unsigned char* As, auto ntn_c, auto diag_c) {
                 constexpr int NTN = decltype(ntn_c)::value;
                 constexpr bool DIAG = decltype(diag_c)::value;   // diagonal block of G: 8 x 8 sub-tiles with nt >= mt only
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < KQ; ++q) {
                     if (!((qmask >> q) & 1)) continue;   // warp-uniform
                     double af[4], bf[NTN];
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) af[mt] = *reinterpret_cast<const double*>(As + a_line + mt * 1024 + off[q]);
+                    for (int mt = 0; mt < 4; ++mt) af[mt] = *reinterpret_cast<const double*>(As + a_line + mt * 1024 + (q >> 2) * HALF_BYTES + off[q & 3]);
 #pragma unroll
-                    for (int nt = 0; nt < NTN; ++nt) bf[nt] = *reinterpret_cast<const double*>(As + b_line + nt * 1024 + off[q]);
+                    for (int nt = 0; nt < NTN; ++nt) bf[nt] = *reinterpret_cast<const double*>(As + b_line + nt * 1024 + (q >> 2) * HALF_BYTES + off[q & 3]);
                     if (WEIGHTED) {
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt) af[mt] *= wcur[q];
@@ -197,7 +212,7 @@ gram_tma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 const int lsn = (ls + 1 == NST) ? 0 : ls + 1;
                 const uint32_t lparn = (ls + 1 == NST) ? (lpar ^ 1u) : lpar;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) wcur[q] = wq[q];
+                for (int q = 0; q < KQ; ++q) wcur[q] = wq[q];
                 if (WEIGHTED && step + 1 < nsteps) load_w(step + 1);
                 switch (ntn) {  // warp-uniform: real branches, never predicated-off DMMAs
                     case 1: ksteps(As, std::integral_constant<int, 1>{}, std::false_type{}); break;
@@ -313,7 +328,7 @@ CUtensorMap make_map(const double* ptr, int64_t rows, int cols, int64_t ld) {
     CUtensorMap tm;
     cuuint64_t gdim[2] = {cuuint64_t(rows), cuuint64_t(cols)};
     cuuint64_t gstr[1] = {cuuint64_t(ld) * 8};
-    cuuint32_t box[2] = {KR, CB};
+    cuuint32_t box[2] = {BOXR, CB};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -416,6 +431,9 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     GramTmaArgs a;
     a.K = K; a.T = T; a.n = n; a.w = dw;
     a.kb = (K + CB - 1) / CB;
+    const int kr = (a.kb + (T + CB - 1) / CB <= MAXSLOTS) ? 32 : 16;   // see stages_for()
+    const int kq = kr / 4;
+    a.kr = kr;
     // job table: cached per shape
     if (ws.jobs_K != K || ws.jobs_T != T) {
         const std::vector<GramJobHost> hj = gram_pack_jobs(K, T);
@@ -440,7 +458,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
                 const int valid = std::min(CB, bb < a.kb ? K - bb * CB : T - (bb - a.kb) * CB);
                 const int ntn = (valid + 7) / 8;
                 const bool diag = (h.tiles[i].first == bb) && ntn == 4;   // upper-triangular sub-tiles only (10 of 16)
-                units.push_back({i, diag ? 10 : 4 * ntn, 0xF, -1, diag ? 5 : ntn});
+                units.push_back({i, diag ? 10 : 4 * ntn, (1 << kq) - 1, -1, diag ? 5 : ntn});
                 order[i] = i;
                 d.slot_a[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].first) - h.blocks.begin());
                 d.slot_b[i] = (unsigned char)(std::find(h.blocks.begin(), h.blocks.end(), h.tiles[i].second) - h.blocks.begin());
@@ -454,11 +472,11 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
                     if (used[sp] < 4 && (best < 0 || load[sp] < load[best])) best = sp;
                 units[i].sp = best;
                 ++used[best];
-                load[best] += units[i].cost * 4;
+                load[best] += units[i].cost * kq;
             }
             auto split = [&](int u, int k, int to) {   // move k of unit u's k4-steps to a new unit on sub-partition `to`
                 int moved = 0, keep = units[u].mask;
-                for (int q = 3; q >= 0 && nq(moved) < k; --q)
+                for (int q = kq - 1; q >= 0 && nq(moved) < k; --q)
                     if ((keep >> q) & 1) { moved |= 1 << q; keep &= ~(1 << q); }
                 units[u].mask = keep;
                 load[units[u].sp] -= units[u].cost * k;
@@ -540,7 +558,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
         const char* e = std::getenv("FRK_GRAM_ITEMS");
         return e ? std::atoi(e) : 0;
     }();
-    auto round_rows = [](int64_t r) { return std::max<int64_t>(KR, (r + KR - 1) / KR * KR); };
+    auto round_rows = [kr](int64_t r) { return std::max<int64_t>(kr, (r + kr - 1) / kr * kr); };
     const int64_t max_split = std::max<int64_t>(1, n / 2048);
     if (a.njobs == 1 || items_env > 0 || max_split < 16) {
         const int per_cta = (a.njobs == 1) ? 1 : (items_env > 0 ? items_env : 6);
@@ -570,13 +588,20 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     FRK_CUDA(cudaGetDevice(&dev));
     bool& attr_set = attr_set_on[dev & 63];
     if (!attr_set) {
-        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(16))));
+        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(16))));
+        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(32))));
+        FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(32))));
         attr_set = true;
     }
     const int grid = std::min(sms, a.nitems);
-    if (dw) gram_tma_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(tmF, tmZ, a);
-    else gram_tma_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(tmF, tmZ, a);
+    if (kr == 16) {
+        if (dw) gram_tma_kernel<true, 16><<<grid, NTHREADS, smem_bytes_for(16), st>>>(tmF, tmZ, a);
+        else gram_tma_kernel<false, 16><<<grid, NTHREADS, smem_bytes_for(16), st>>>(tmF, tmZ, a);
+    } else {
+        if (dw) gram_tma_kernel<true, 32><<<grid, NTHREADS, smem_bytes_for(32), st>>>(tmF, tmZ, a);
+        else gram_tma_kernel<false, 32><<<grid, NTHREADS, smem_bytes_for(32), st>>>(tmF, tmZ, a);
+    }
     FRK_CUDA(cudaGetLastError());
     gram_tma_reduce_kernel<<<a.njobs * NWARPS * (TILE_DOUBLES / RED_ELEMS), RED_ELEMS * RED_GROUPS, 0, st>>>(a, ws.zzpart.p, nzz,
                                                                                                           dpacked);
