@@ -157,3 +157,38 @@ def test_second_device_in_one_process():
         _lib.check(_lib.lib.frk_set_device(0))
     for a, b in zip(results[0], results[1]):
         assert np.array_equal(np.asarray(a), np.asarray(b))      # same code, same inputs: bitwise equal across devices
+
+
+def test_bitwise_repeatability():
+    """The dynamic work queue of the Gram kernel and the persistent tiles of K1 must not leak into the results:
+    two runs on the same inputs are bitwise equal (partials are reduced in a fixed order, no atomics on data)."""
+    import ctypes as C
+    import torch
+    from autofrk_b200 import _lib, mrts as G
+
+    rng = np.random.default_rng(8)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    n, K, T = 1_000_003, 300, 40
+    F = torch.randn((K, n + 1), dtype=torch.float64, device="cuda", generator=g).T
+    Z = torch.randn((T, n + 1), dtype=torch.float64, device="cuda", generator=g).T
+    w = torch.rand(n + 1, dtype=torch.float64, device="cuda", generator=g)
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for wt in (None, w):
+        runs = []
+        for _ in range(3):
+            p = torch.empty(plen, dtype=torch.float64, device="cuda")
+            _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, n + 1, C.c_void_p(Z.data_ptr()), T, n + 1,
+                                                   None if wt is None else C.c_void_p(wt.data_ptr()), C.c_void_p(p.data_ptr()), st))
+            runs.append(p)
+        torch.cuda.synchronize()
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    d, m, kstar = 2, 600, 330
+    Xu = rng.random((m, d))
+    UZ = np.zeros((m + d + 1, kstar + d + 1))
+    UZ[:m, :kstar] = rng.standard_normal((m, kstar))
+    plan = G.MrtsPlan(Xu, rng.standard_normal((d + 1, m)), UZ, np.ones(d), kstar)
+    x = torch.rand((d, 300_001), dtype=torch.float64, device="cuda", generator=g).T
+    a, b = plan.predict_dev(x), plan.predict_dev(x)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
