@@ -1,4 +1,4 @@
-"""In-tree build of libfrk_b200.so (nvcc, sm_100a only) and of the plain-C oracle library.
+"""In-tree build of libfrk_b200.so (nvcc, sm_100a only).  (The checker builds itself: oracle/build_oracle.py.)
 
 `python -m autofrk_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
 Objects are rebuilt only when a source or header is newer (so repeated calls are cheap).
@@ -63,21 +63,10 @@ def build_cuda(verbose: bool = False, force: bool = False) -> Path:
     return LIB
 
 
-def build_oracle() -> Path:
-    """The oracle is test infrastructure; building the checker is not using it."""
-    odir = ROOT / "oracle"
-    lib = odir / "libfrk_oracle.so"
-    src = odir / "tps_scalar.c"
-    if _stale(lib, [src]):
-        _run([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-o", str(lib), str(src), "-lm"])
-    return lib
-
-
 def main():
     verbose = "-v" in sys.argv
     force = "-f" in sys.argv
     print(build_cuda(verbose=verbose, force=force))
-    print(build_oracle())
 
 
 if __name__ == "__main__":

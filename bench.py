@@ -85,9 +85,9 @@ def cpu_predict_rows(Xu, UZ, BBBH, nconst, xnew, K, threads):
     (src/autoFRK.cpp:109-153, one row block per host thread), BLAS GEMM for the projection (:316-324)."""
     import ctypes as C
 
-    from autofrk_b200 import build
+    from oracle.build_oracle import build_oracle
 
-    lib = C.CDLL(str(build.build_oracle()))
+    lib = C.CDLL(str(build_oracle()))
     lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_int64]
     n2_all, d = xnew.shape

@@ -15,10 +15,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", autouse=True)
 def _built_libraries():
-    """The CUDA library and the C oracle are built in-tree (nvcc cross-compiles without a GPU)."""
+    """The CUDA library and the checker libraries are built in-tree (nvcc cross-compiles without a GPU)."""
     from autofrk_b200 import build
 
     if not build.LIB.exists() or os.environ.get("FRK_REBUILD"):
         build.build_cuda()
-    build.build_oracle()
+    from oracle import build_oracle as ob
+
+    ob.build_oracle()
+    ob.build_ref()          # the reference's own translation unit (built where /root/reference exists; travels prebuilt)
     yield

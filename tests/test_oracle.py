@@ -18,9 +18,9 @@ ROOT = Path(__file__).resolve().parent.parent
 
 @pytest.fixture(scope="module")
 def clib():
-    from autofrk_b200 import build
+    from oracle.build_oracle import build_oracle
 
-    lib = C.CDLL(str(build.build_oracle()))
+    lib = C.CDLL(str(build_oracle()))
     lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
     lib.oracle_tpm2.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.oracle_predict_x1.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
