@@ -58,6 +58,7 @@ _SIGNATURES = {
     "frk_gram_stats": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "frk_gram_packed_len": (_i64, [_i32, _i32]),
     "frk_gram_job_plan": (_i64, [_i32, _i32, _vp, _vp, _i64]),
+    "frk_gram_mid_plan": (_i64, [_i32, _i32, _vp, _vp, _vp, _i64]),
     "frk_gram_stats_dev": (_i32, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp]),
     "frk_plan_predict_gram_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _i64, _vp]),
     "frk_peer_sum_dev": (_i32, [_vp, _i32, _i64, _vp, _vp]),

@@ -113,6 +113,23 @@ int64_t frk_gram_job_plan(int32_t K, int32_t T, int32_t* njobs, int32_t* triples
     return count;
 }
 
+int64_t frk_gram_mid_plan(int32_t K, int32_t T, int32_t* nsets, int32_t* sp_load, int32_t* tiles, int64_t cap) {
+    frk::GramMidPlan P;
+    if (!frk::gram_mid_plan(K, T, P)) return -1;
+    if (nsets) *nsets = P.nsets;
+    if (sp_load)
+        for (int p = 0; p < 4; ++p) sp_load[p] = P.sp_load[p];
+    for (size_t i = 0; tiles && i < P.tiles.size() && int64_t(i) < cap; ++i) {
+        const frk::GramMidTile& t = P.tiles[i];
+        tiles[5 * i + 0] = t.ga;
+        tiles[5 * i + 1] = t.gb;
+        tiles[5 * i + 2] = t.isz;
+        tiles[5 * i + 3] = t.warp;
+        tiles[5 * i + 4] = t.slot;
+    }
+    return int64_t(P.tiles.size());
+}
+
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,
                            int64_t ldz, const double* d_weights, double* d_packed, void* stream) {
     return guarded([&] {

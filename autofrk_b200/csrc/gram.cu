@@ -272,6 +272,16 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     FRK_CUDA(cudaGetDevice(&dev));
     FRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
+    const char* const path_c = std::getenv("FRK_GRAM_PATH");   // tuning / test aid: cpasync | tma | narrow (default: best fit)
+    const std::string path_env(path_c ? path_c : "");
+    const bool force_cpasync = path_env == "cpasync";
+    const bool force_wide = force_cpasync || path_env == "tma";
+    if (path_env.empty() && gram_stats_mid_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, st)) {
+        ws.launches += 2;
+        ws.last_path = "mid";
+        return;
+    }
+
     const int nzz = 512;
     if (ws.zzpart.n < size_t(nzz)) ws.zzpart.alloc(nzz);
     if (T > 0) {
@@ -283,21 +293,15 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     }
     FRK_CUDA(cudaGetLastError());
 
-    static const bool force_cpasync = [] {
-        const char* e = std::getenv("FRK_GRAM_PATH");
-        return e && std::string(e) == "cpasync";
-    }();
-    static const bool force_wide = [] {
-        const char* e = std::getenv("FRK_GRAM_PATH");
-        return e && (std::string(e) == "cpasync" || std::string(e) == "tma");
-    }();
     if (!force_wide && gram_stats_narrow_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st)) {
         ws.launches += 3;
+        ws.last_path = "narrow";
         return;
     }
     if (!force_cpasync && gram_tma_usable(dF, ldf, dZ, T, ldz, n)) {
         gram_stats_tma_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st);
         ws.launches += 3;
+        ws.last_path = "tma";
         return;
     }
     {
@@ -347,6 +351,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         ws.last_nsplit = a.nsplit;
         ws.last_npairs = a.npairs;
     }
+    ws.last_path = "cpasync";
     ws.launches += 3;
 }
 

@@ -122,6 +122,12 @@ int64_t frk_gram_packed_len(int32_t K, int32_t T);
  * (job, block_a, block_b) to `triples` (may be NULL) and returns the number of pairs; *njobs receives the job
  * count.  No device work. */
 int64_t frk_gram_job_plan(int32_t K, int32_t T, int32_t* njobs, int32_t* triples, int64_t cap);
+/* The same for the register-resident kernel that takes the shapes default autoFRK() selects (K + T <= 256 columns):
+ * 8 x 8 output tiles dealt to 16 warps.  Writes up to `cap` quintuples (row group, column group, is_Z, warp,
+ * accumulator slot) to `tiles` (may be NULL), the number of row-stage sets (1, 2 or 4) to *nsets and the DMMAs per
+ * k4-step that land on each of the four SM sub-partitions to sp_load[4]; returns the tile count, or -1 when the
+ * shape does not fit this kernel.  No device work. */
+int64_t frk_gram_mid_plan(int32_t K, int32_t T, int32_t* nsets, int32_t* sp_load, int32_t* tiles, int64_t cap);
 /* device pointers: F n x K (ld ldf), Z n x T (ld ldz) -> d_packed; asynchronous on `stream`.
  * Multi-GPU: every rank calls this on its row shard, then one allreduce(sum) of d_packed. */
 int32_t frk_gram_stats_dev(const double* d_F, int64_t n, int32_t K, int64_t ldf, const double* d_Z, int32_t T,

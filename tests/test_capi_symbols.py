@@ -87,3 +87,33 @@ def test_gram_job_plan_covers_every_block_pair_once():
         # never more work than the 128-column tiling it replaced (16 warp tiles per tile pair, 10 on the diagonal)
         ntf, ntz = -(-K // 128), -(-T // 128)
         assert count <= 10 * ntf + 16 * (ntf * (ntf - 1) // 2 + ntf * ntz)
+
+
+def test_gram_mid_plan_covers_every_tile_once_and_balances_the_pipes():
+    """Host-side plan of the register-resident Gram kernel (no device): every 8 x 8 tile of the upper triangle of F'F
+    and of F'Z is held by exactly one (warp, accumulator slot); the four SM sub-partitions issue the same number of
+    DMMAs (within one per k4-step); shapes that do not fit are declined."""
+    import numpy as np
+    from autofrk_b200 import _lib
+
+    lib = _lib.lib
+    lib.frk_gram_mid_plan.restype = ctypes.c_int64
+    for K in list(range(1, 129)) + [129, 200, 256]:
+        for T in (0, 1, 4, 16, 20, 32, 33, 100):
+            ns = ctypes.c_int32(0)
+            sp = (ctypes.c_int32 * 4)()
+            cnt = lib.frk_gram_mid_plan(K, T, ctypes.byref(ns), sp, None, 0)
+            MT, NZ = -(-K // 8), -(-T // 8)
+            kb, zb = -(-K // 32), -(-T // 32)
+            if cnt < 0:
+                assert K > 128 or T > 32, (K, T)      # every K <= 128 with T <= 32 fits: 32 units, 8 column blocks
+                continue
+            tiles = np.zeros((cnt, 5), dtype=np.int32)
+            assert lib.frk_gram_mid_plan(K, T, ctypes.byref(ns), sp, tiles.ctypes.data, cnt) == cnt
+            want = {(a, b, 0) for a in range(MT) for b in range(a, MT)} | {(a, z, 1) for a in range(MT) for z in range(NZ)}
+            got = [(int(a), int(b), int(z)) for a, b, z, _, _ in tiles]
+            assert len(got) == len(set(got)) and set(got) == want, (K, T)
+            holders = [(int(w), int(s)) for _, _, _, w, s in tiles]
+            assert len(set(holders)) == cnt and all(0 <= w < 16 // ns.value and 0 <= s < 16 for w, s in holders), (K, T)
+            assert ns.value in (1, 2, 4) and sum(sp) == cnt * ns.value
+            assert max(sp) - min(sp) <= 2, (K, T, list(sp))

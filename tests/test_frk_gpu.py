@@ -416,13 +416,26 @@ def _frk_error():
     return FrkError
 
 
+@pytest.mark.parametrize("path", ["", "mid:tensor", "mid:cpasync", "narrow", "tma", "cpasync"])
 @pytest.mark.parametrize("n,K,T,weighted", [(100_003, 32, 4, False), (50_000, 5, 1, True), (77_777, 48, 8, False),
-                                             (20_001, 17, 0, False), (64_000, 40, 16, True), (999, 3, 2, False)])
-def test_gram_narrow_variant(n, K, T, weighted):
-    """few basis functions: the register-tile kernel (gram_narrow.cu) through the device entry point."""
+                                             (20_001, 17, 0, False), (64_000, 40, 16, True), (999, 3, 2, False),
+                                             (70_001, 64, 4, False), (33_333, 100, 1, True), (41_000, 128, 16, False),
+                                             (9_000, 128, 32, True), (130, 72, 20, False), (31, 100, 3, True),
+                                             (50_000, 96, 0, False), (25_000, 40, 100, False)])
+def test_gram_small_K_variants(n, K, T, weighted, path, monkeypatch):
+    """The shapes default autoFRK() selects (K <= ~130), through the device entry point: the register-resident kernel
+    (gram_mid.cu: 1, 2 and 4 row-stage sets, ragged rows and columns, row weights, zz folded in) and, forced through
+    FRK_GRAM_PATH, the kernels it stands in front of (gram_narrow.cu for K <= 48, the job kernel, the cp.async one)."""
     import ctypes as C
     import torch
     from autofrk_b200 import _lib
+
+    monkeypatch.delenv("FRK_GRAM_PATH", raising=False)
+    monkeypatch.delenv("FRK_GRAM_MID_STAGING", raising=False)
+    if path.startswith("mid:"):      # the register-resident kernel with either staging mode (2-D TMA boxes / cp.async)
+        monkeypatch.setenv("FRK_GRAM_MID_STAGING", path[4:])
+    elif path:
+        monkeypatch.setenv("FRK_GRAM_PATH", path)
 
     g = torch.Generator(device="cuda").manual_seed(n)
     ld = n + (n & 1)

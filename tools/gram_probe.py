@@ -9,7 +9,14 @@ sys.path.insert(0, ".")
 from autofrk_b200 import _lib
 
 
-def run(n, K, T, reps=3):
+def run(n, K, T, reps=3, path=""):
+    import os
+    os.environ.pop("FRK_GRAM_PATH", None)
+    os.environ.pop("FRK_GRAM_MID_STAGING", None)
+    if path.startswith("mid:"):
+        os.environ["FRK_GRAM_MID_STAGING"] = path[4:]
+    elif path:
+        os.environ["FRK_GRAM_PATH"] = path
     F = torch.randn((K, n), dtype=torch.float64, device="cuda").T
     Z = torch.randn((max(T, 1), n), dtype=torch.float64, device="cuda").T
     plen = _lib.lib.frk_gram_packed_len(K, T)
@@ -27,13 +34,20 @@ def run(n, K, T, reps=3):
         e0.record(); go(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     flops = n * K * (K + 1.0) + 2.0 * n * K * T + 2.0 * n * T
-    res = dict(n=n, K=K, T=T, ms=best, tflops_credited=flops / best / 1e9, gbs=8.0 * n * (K + T) / best / 1e6)
+    res = dict(n=n, K=K, T=T, path=path or "default", ms=best, tflops_credited=flops / best / 1e9, gbs=8.0 * n * (K + T) / best / 1e6)
     print(json.dumps(res), flush=True)
     return res
 
 
 if __name__ == "__main__":
-    out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(5_000_000, 32, 4), run(1_000_000, 1000, 100),
-           run(5_000_000, 200, 20), run(5_000_000, 256, 1), run(5_000_000, 100, 1), run(5_000_000, 64, 4),
-           run(2_000_000, 446, 1)]
+    out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(1_000_000, 1000, 100),
+           run(5_000_000, 200, 20), run(5_000_000, 256, 1), run(2_000_000, 446, 1)]
+    # shapes default autoFRK() selects (K = 18 ... ~130): the register-resident kernel against the ones it replaces
+    for K, T in ((16, 1), (32, 4), (48, 8), (64, 4), (64, 1), (100, 1), (128, 4), (128, 16), (100, 20)):
+        out.append(run(5_000_000, K, T))
+        out.append(run(5_000_000, K, T, path="mid:tensor"))
+        out.append(run(5_000_000, K, T, path="mid:cpasync"))
+        if K <= 48 and T <= 16:
+            out.append(run(5_000_000, K, T, path="narrow"))
+        out.append(run(5_000_000, K, T, path="tma"))
     json.dump(out, open("gpurun_out/gram_probe.json", "w"), indent=1)

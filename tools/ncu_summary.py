@@ -33,15 +33,29 @@ for r in rows[2:]:
             print(f"{k:95s} {r[i]} {units[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-h = rows[1]
-idx = {n: i for i, n in enumerate(h)}
-data = [r for r in rows[2:] if len(r) == len(h)]
-tot = sum(int(r[idx["# Samples"]]) for r in data)
-print(f"\nsource page: {len(data)} SASS instructions, {tot} warp-state samples; top {topn} by samples")
-stall_cols = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
-agg = {c: sum(int(r[idx[c]] or 0) for r in data) for c in stall_cols}
-print("stall totals:", {k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]})
-for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]]))[:topn]:
-    st = {c: int(r[idx[c]]) for c in stall_cols if r[idx[c]] not in ("", "0")}
-    st = dict(sorted(st.items(), key=lambda kv: -kv[1])[:2])
-    print(f"{int(r[idx['# Samples']]):7d} {100.0 * int(r[idx['# Samples']]) / tot:5.1f}%  {r[1].strip()[:64]:64s} {st}")
+# one block per profiled launch: a "Kernel Name" row, a header row, then the SASS lines
+blocks, cur = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1] if len(r) > 1 else "", "h": None, "data": []}
+        blocks.append(cur)
+    elif cur is not None and cur["h"] is None:
+        cur["h"] = r
+    elif cur is not None and len(r) == len(cur["h"]):
+        cur["data"].append(r)
+for bi, b in enumerate(blocks):
+    h, data = b["h"], b["data"]
+    idx = {n: i for i, n in enumerate(h)}
+    tot = sum(int(r[idx["# Samples"]]) for r in data) or 1
+    print(f"\nsource page, launch {bi}: {b['name'][:90]}\n{len(data)} SASS instructions, {tot} warp-state samples; top {topn} by samples")
+    stall_cols = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+    agg = {c: sum(int(r[idx[c]] or 0) for r in data) for c in stall_cols}
+    print("stall totals:", {k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]})
+    if "L1 Wavefronts Shared Excessive" in idx:
+        exc = [(int(r[idx["L1 Wavefronts Shared Excessive"]] or 0), r[1].strip()[:70]) for r in data]
+        exc = sorted([e for e in exc if e[0] > 0], reverse=True)[:8]
+        print("shared-memory excessive wavefronts (bank conflicts) by instruction:", exc if exc else "none")
+    for r in sorted(data, key=lambda r: -int(r[idx["# Samples"]]))[:topn]:
+        st = {c: int(r[idx[c]]) for c in stall_cols if r[idx[c]] not in ("", "0")}
+        st = dict(sorted(st.items(), key=lambda kv: -kv[1])[:2])
+        print(f"{int(r[idx['# Samples']]):7d} {100.0 * int(r[idx['# Samples']]) / tot:5.1f}%  {r[1].strip()[:64]:64s} {st}")
