@@ -272,11 +272,16 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     FRK_CUDA(cudaGetDevice(&dev));
     FRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-    const char* const path_c = std::getenv("FRK_GRAM_PATH");   // tuning / test aid: cpasync | tma | narrow (default: best fit)
+    const char* const path_c = std::getenv("FRK_GRAM_PATH");   // tuning / test aid: mid | narrow | tma | cpasync (default: best fit)
     const std::string path_env(path_c ? path_c : "");
     const bool force_cpasync = path_env == "cpasync";
     const bool force_wide = force_cpasync || path_env == "tma";
-    if (path_env.empty() && gram_stats_mid_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, st)) {
+    // K <= 16: the whole tile set is a handful of accumulators and the pass is pure streaming -- the direct-from-global
+    // register kernel (gram_narrow.cu) wins (0.23 vs 0.29 ms at n = 5e6, K = 16, T = 1); from K = 32 on the
+    // register-resident kernel is as fast or faster and needs no separate pass over Z
+    const bool prefer_narrow = path_env == "narrow" || (path_env.empty() && K <= 16 && T <= 16);
+    if ((path_env.empty() || path_env == "mid") && !prefer_narrow &&
+        gram_stats_mid_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, st)) {
         ws.launches += 2;
         ws.last_path = "mid";
         return;
@@ -293,7 +298,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     }
     FRK_CUDA(cudaGetLastError());
 
-    if (!force_wide && gram_stats_narrow_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st)) {
+    if (!force_wide && path_env != "mid" && gram_stats_narrow_dev(dF, n, K, ldf, dZ, T, ldz, dw, dpacked, ws, sms, nzz, st)) {
         ws.launches += 3;
         ws.last_path = "narrow";
         return;

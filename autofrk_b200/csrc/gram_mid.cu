@@ -15,7 +15,14 @@
 //   * rows arrive as for the wide kernel: cp.async.bulk.tensor.2d boxes of [32 columns][16 rows] with SWIZZLE_128B
 //     (conflict-free fragment LDS.64 under the permuted k order), 32 rows per stage, a ring of up to 12 stages,
 //     `full` mbarriers, last-finisher re-arm, no CTA barrier in the loop; ragged rows / columns are zero-filled by
-//     the TMA unit;
+//     the TMA unit.  Staging alternatives were measured and dropped (tools/tma_stream_bench.cu,
+//     profiles/tma_stream_bench_r02.json, profiles/gram_probe_r02_v3..v6): one CTA per SM streaming this column-major
+//     pattern with such boxes and no arithmetic reaches 3.6 TB/s (32-row stages) to 4.9 TB/s (128-row stages, row
+//     boxes of a column block issued together) against 7.0 TB/s for a plain LDG.128 read; per-column 1-D bulk
+//     copies cost >= 65 clocks each and need 2 KB per copy (two 75 KB stages: too coarse a ring once the arithmetic
+//     holds a stage -- 3.5 TB/s with a 14-clock-per-row hold); cp.async from the warp that re-arms a stage puts
+//     18 .. 72 LDGSTS on the ring's critical path (2x slower); 64 / 128-row stages made every set wait for whole
+//     stages and lost more than the longer runs gained;
 //   * zz is accumulated from the Z boxes already in shared memory by one warp of the stage's set (in rotation);
 //   * one persistent CTA per SM owns a contiguous row range; partial tiles go to a workspace and a second kernel
 //     adds them in a fixed order (bitwise reproducible) and mirrors G.
@@ -45,8 +52,6 @@ constexpr int MNU = GRAM_MID_UNITS;        // units per warp
 constexpr int MAXBLK = 8;
 constexpr int MAXST = 12;
 constexpr size_t MID_SMEM_BUDGET = 200 * 1024;
-constexpr size_t MIDB_SMEM_BUDGET = 222 * 1024;   // cp.async staging uses all the shared memory an SM has
-constexpr int GRAM_MID_CP_MAXCOLS = 200;            // wider shapes are tensor-pipe bound: the 2-D TMA boxes cost no issue slots
 
 struct MidArgs {
     int K, T, kb, nblocks, nst, nsets, ntiles;
@@ -268,235 +273,6 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     }
 }
 
-
-// ---- cp.async staging ----------------------------------------------------------------------------------------------
-// Measured on this pool's B200 (profiles/tma_stream_bench_r02.json, tools/tma_stream_bench.cu): one CTA per SM
-// streaming this column-major pattern with swizzled 2-D TMA boxes tops out at 4.4-4.6 TB/s (the TMA unit spends ~8
-// clocks per 128-byte box row); per-column 1-D bulk copies cost >= 65 clocks each, so only >= 2 KB copies reach the
-// read-only ceiling (6.8 TB/s; LDG.128: 7.0 TB/s) -- but then two 75 KB stages are all that fits, and with the slot
-// handed back only after the arithmetic the copies in flight fall to one stage and the rate to 3.5 TB/s (measured with
-// a hold of 14 clocks per row standing in for the DMMAs).  What the HBM-bound shapes need is MANY SMALL stages, i.e.
-// ~200 KB in flight per SM whatever is being consumed.  So few-column shapes are staged by cp.async (LDGSTS.128, the
-// LSU path): 32 rows per stage as [column][32 + 4 rows] (the + 4 doubles make the fragment LDS.64 of eight adjacent
-// columns conflict free with the natural k order), up to 24 stages, completion through cp.async.mbarrier.arrive on the
-// stage's `full` barrier, ragged rows zero-filled by the copy's src-size operand.  The warp that is last to finish a
-// stage re-arms it (one 16-byte copy per lane and instruction; 18 instructions at K = 32, T = 4).
-constexpr int MCP_PITCH = (MKR + 4) * 8;     // bytes per column of a stage
-constexpr int MCP_MAXST = 24;
-
-struct MidBArgs {
-    const double* F;
-    const double* Z;
-    const double* w;
-    int64_t ldf, ldz, n, rows_cta;
-    int K, T, nst, nsets, ntiles, ncols;    // ncols = K + T (+ 1 weights) + 1 zero column
-    const GramMidUnit* units;
-    double* partial;
-    double* zzcta;
-};
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int NR, int NC, bool TRI, bool WEIGHTED>
-__device__ __forceinline__ void midb_unit(const uint32_t (&pa)[2], const uint32_t (&pb)[4], uint32_t rowoff, uint32_t wa,
-                                          double (&acc)[2][4][2]) {
-#pragma unroll
-    for (int q = 0; q < MKQ; ++q) {
-        double af[NR], bf[NC];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) af[i] = lds_f64(pa[i] + rowoff + q * 32);
-#pragma unroll
-        for (int j = 0; j < NC; ++j) bf[j] = lds_f64(pb[j] + rowoff + q * 32);
-        if (WEIGHTED) {
-            const double wv = lds_f64(wa + rowoff + q * 32);
-#pragma unroll
-            for (int i = 0; i < NR; ++i) af[i] *= wv;
-        }
-#pragma unroll
-        for (int i = 0; i < NR; ++i)
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-                if (!(TRI && i == 1 && j == 0)) dmma_m(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-}
-
-template <bool WEIGHTED>
-__device__ __forceinline__ void midb_unit_dispatch(int kind, const uint32_t (&pa)[2], const uint32_t (&pb)[4], uint32_t rowoff,
-                                                   uint32_t wa, double (&acc)[2][4][2]) {
-    switch (kind) {   // warp-uniform
-#define FRK_MIDB_CASE(id, NR, NC, TRI) \
-    case id: midb_unit<NR, NC, TRI, WEIGHTED>(pa, pb, rowoff, wa, acc); break;
-        FRK_MIDB_CASE(1, 1, 1, false) FRK_MIDB_CASE(2, 1, 2, false) FRK_MIDB_CASE(3, 1, 3, false) FRK_MIDB_CASE(4, 1, 4, false)
-        FRK_MIDB_CASE(5, 2, 1, false) FRK_MIDB_CASE(6, 2, 2, false) FRK_MIDB_CASE(7, 2, 3, false) FRK_MIDB_CASE(8, 2, 4, false)
-        FRK_MIDB_CASE(GRAM_MID_TRI24, 2, 4, true) FRK_MIDB_CASE(GRAM_MID_TRI22, 2, 2, true)
-#undef FRK_MIDB_CASE
-        default: break;
-    }
-}
-
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(MNT, 1) gram_midb_kernel(const MidBArgs a) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* const base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const int stage_bytes = a.ncols * MCP_PITCH;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(base + size_t(a.nst) * stage_bytes);
-    uint32_t* const done = reinterpret_cast<uint32_t*>(full + MCP_MAXST);
-    double* const zzw = reinterpret_cast<double*>(done + MCP_MAXST);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int wps = MNW / a.nsets;
-    const int set = warp / wps;
-    const int rot = (a.nsets == 4) ? 1 : (a.nsets == 2 ? 2 : 0);
-    const int jlog = ((warp - set * wps) - set * rot % wps + wps) % wps;
-    // column slots of a stage: F columns, Z columns, [weights], one column of zeros (stands in for columns >= K / >= T)
-    const int wcol = a.K + a.T, zerocol = a.ncols - 1;
-
-    // per unit: byte offsets inside a stage of this lane's column of every fragment (+ its k row t)
-    int kd[MNU];
-    uint32_t oa[MNU][2], ob[MNU][4];
-#pragma unroll
-    for (int u = 0; u < MNU; ++u) {
-        const GramMidUnit x = a.units[jlog * MNU + u];
-        kd[u] = x.kind;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c = (x.ga0 + i) * 8 + g;
-            oa[u][i] = uint32_t((c < a.K ? c : zerocol) * MCP_PITCH + t * 8);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = (x.gb0 + j) * 8 + g;
-            const int col = x.isz ? (c < a.T ? a.K + c : zerocol) : (c < a.K ? c : zerocol);
-            ob[u][j] = uint32_t(col * MCP_PITCH + t * 8);
-        }
-    }
-    bool active = false;
-#pragma unroll
-    for (int u = 0; u < MNU; ++u) active = active || (kd[u] != 0);
-    int nact = 0, myrank = 0;   // active warps of a set, this warp's rank among them (zz duty)
-    for (int j = 0; j < wps; ++j) {
-        bool act = false;
-        for (int u = 0; u < MNU; ++u) act = act || (__ldg(&a.units[j * MNU + u].kind) != 0);
-        if (act && j < jlog) ++myrank;
-        nact += act ? 1 : 0;
-    }
-
-    if (tid == 0) {
-        for (int s = 0; s < a.nst; ++s) {
-            mbar_init(&full[s], 32);     // one cp.async.mbarrier.arrive per lane of the arming warp
-            done[s] = 0;
-        }
-        mbar_fence_init();
-    }
-    for (int s = 0; s < a.nst; ++s)   // the zero column of every stage (never written again)
-        for (int e = tid; e < MCP_PITCH / 8; e += MNT) reinterpret_cast<double*>(base + size_t(s) * stage_bytes + size_t(zerocol) * MCP_PITCH)[e] = 0.0;
-    __syncthreads();
-
-    const int64_t r_begin = min(a.n, int64_t(blockIdx.x) * a.rows_cta);
-    const int64_t r_end = min(a.n, r_begin + a.rows_cta);
-    const int nsteps = (r_end > r_begin) ? int((r_end - r_begin + MKR - 1) / MKR) : 0;
-    const int ndata = a.K + a.T + (WEIGHTED ? 1 : 0);     // columns that are copied
-    const int ncopies = ndata * (MKR / 2);                 // 16-byte pieces of a stage
-    auto issue = [&](int slot, int step) {   // one whole warp: lane -> consecutive 16-byte pieces of a column
-        const uint32_t dst = smem_u32(base + size_t(slot) * stage_bytes);
-        const int64_t r0 = r_begin + int64_t(step) * MKR;
-        for (int e = lane; e < ncopies; e += 32) {
-            const int c = e / (MKR / 2), rp = e % (MKR / 2);
-            const double* col = c < a.K ? a.F + int64_t(c) * a.ldf : (c < a.K + a.T ? a.Z + int64_t(c - a.K) * a.ldz : a.w);
-            const int64_t r = r0 + 2 * rp;
-            const int bytes = int(max(int64_t(0), min(int64_t(2), r_end - r))) * 8;   // rows past the end are zero-filled
-            cp_async16_zfill(dst + uint32_t(c * MCP_PITCH + rp * 16), bytes > 0 ? col + r : col, bytes);
-        }
-        cp_async_mbar_arrive_noinc(&full[slot]);
-    };
-    if (warp == 0)
-        for (int i = 0; i < a.nst && i < nsteps; ++i) issue(i, i);
-
-    double acc[MNU][2][4][2];
-#pragma unroll
-    for (int u = 0; u < MNU; ++u)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[u][i][j][0] = acc[u][i][j][1] = 0.0;
-    double zz = 0.0;
-
-    if (active) {
-        int slot = set % a.nst;
-        uint32_t par = uint32_t(set / a.nst) & 1u;
-        int duty = 0;
-        const uint32_t wofs = uint32_t(wcol * MCP_PITCH + t * 8);
-        for (int step = set; step < nsteps; step += a.nsets) {
-            mbar_wait(&full[slot], par);
-            const uint32_t As = smem_u32(base + size_t(slot) * stage_bytes);
-#pragma unroll
-            for (int u = 0; u < MNU; ++u) {
-                uint32_t pa[2], pb[4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) pa[i] = As + oa[u][i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pb[j] = As + ob[u][j];
-                midb_unit_dispatch<WEIGHTED>(kd[u], pa, pb, 0u, As + wofs, acc[u]);
-            }
-            if (a.T > 0 && duty % nact == myrank) {   // this stage's z^2: 16-byte pieces (two rows) of the Z columns
-                const int nchunks = a.T * (MKR / 2);
-                for (int e = lane; e < nchunks; e += 32) {
-                    const int c = e / (MKR / 2), rp = e % (MKR / 2);
-                    double2 v;
-                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(As + uint32_t((a.K + c) * MCP_PITCH + rp * 16)));
-                    if (WEIGHTED) {
-                        double2 wv;
-                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(wv.x), "=d"(wv.y) : "r"(As + uint32_t(wcol * MCP_PITCH + rp * 16)));
-                        zz += fma(wv.x * v.x, v.x, (wv.y * v.y) * v.y);
-                    } else {
-                        zz += fma(v.x, v.x, v.y * v.y);
-                    }
-                }
-            }
-            ++duty;
-            __syncwarp();
-            uint32_t last = 0;
-            if (lane == 0) last = (smem_add_relaxed(&done[slot], 1u) == uint32_t(nact - 1)) ? 1u : 0u;
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                if (lane == 0) done[slot] = 0;
-                if (step + a.nst < nsteps) issue(slot, step + a.nst);
-            }
-            slot += a.nsets;
-            while (slot >= a.nst) {
-                slot -= a.nst;
-                par ^= 1u;
-            }
-        }
-    }
-
-    double* const out = a.partial + (size_t(blockIdx.x) * MNW + warp) * (MNU * 8 * 64);
-#pragma unroll
-    for (int u = 0; u < MNU; ++u)
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (kd[u] != 0) {
-                    double2* p = reinterpret_cast<double2*>(out + ((u * 8 + i * 4 + j) * 64 + g * 8 + 2 * t));
-                    *p = make_double2(acc[u][i][j][0], acc[u][i][j][1]);
-                }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) zz += __shfl_xor_sync(0xffffffffu, zz, o);
-    if (lane == 0) zzw[warp] = zz;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int wv = 0; wv < MNW; ++wv) s += zzw[wv];
-        a.zzcta[blockIdx.x] = s;
-    }
-}
 
 // One block per 8 x 8 output tile: four thread groups each add every fourth CTA's partials (all sets of a CTA in
 // set order), combined as (s0 + s1) + (s2 + s3); block 0 also adds the per-CTA sums of squares in CTA order.
@@ -720,51 +496,12 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     FRK_CUDA(cudaGetDevice(&dev));
     static std::once_flag once[64];   // the opt-in to large dynamic shared memory is per device
     std::call_once(once[dev & 63], [] {
-        const int cap = int(MIDB_SMEM_BUDGET + 2048);
+        const int cap = int(MID_SMEM_BUDGET + 2048);
         FRK_CUDA(cudaFuncSetAttribute(gram_mid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         FRK_CUDA(cudaFuncSetAttribute(gram_mid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        FRK_CUDA(cudaFuncSetAttribute(gram_midb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        FRK_CUDA(cudaFuncSetAttribute(gram_midb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     });
     const GramMidTile* dtiles = reinterpret_cast<const GramMidTile*>(reinterpret_cast<const unsigned char*>(ws.mid_tab.p) +
                                                                     sizeof(GramMidUnit) * MNW * MNU);
-    // few columns (the HBM-bound end): cp.async staging, as many 32-row stages as fit (see gram_midb_kernel)
-    const int ncols_b = K + T + (dw ? 1 : 0) + 1;
-    const char* const stage_env = std::getenv("FRK_GRAM_MID_STAGING");     // tuning / test aid: "tensor" | "cpasync"
-    const size_t stage_b = size_t(ncols_b) * MCP_PITCH;
-    bool use_cp = ncols_b <= GRAM_MID_CP_MAXCOLS;
-    if (stage_env && std::string(stage_env) == "tensor") use_cp = false;
-    if (stage_env && std::string(stage_env) == "cpasync") use_cp = true;
-    if (dw && reinterpret_cast<uintptr_t>(dw) % 16) use_cp = false;
-    int nst_b = int(std::min<size_t>(MCP_MAXST, MIDB_SMEM_BUDGET / stage_b));
-    nst_b -= nst_b % ws.mid_nsets;          // a ring slot is always consumed by the same set
-    if (nst_b < 2 * ws.mid_nsets) use_cp = false;
-    if (use_cp) {
-        MidBArgs b;
-        b.F = dF; b.Z = dZ; b.w = dw; b.ldf = ldf; b.ldz = ldz; b.n = n;
-        b.K = K; b.T = T; b.ncols = ncols_b;
-        b.nsets = ws.mid_nsets;
-        b.ntiles = ws.mid_ntiles;
-        b.nst = nst_b;
-        const size_t smem = size_t(b.nst) * stage_b + 128 + MCP_MAXST * 8 + MCP_MAXST * 4 + MNW * 8 + 64;
-        const int grid = int(std::max<int64_t>(1, std::min<int64_t>(sms, (n + 8 * MKR - 1) / (8 * MKR))));
-        b.rows_cta = ((n + grid - 1) / grid + MKR - 1) / MKR * MKR;
-        b.units = reinterpret_cast<const GramMidUnit*>(ws.mid_tab.p);
-        const size_t need = size_t(grid) * MNW * MNU * 8 * 64 + size_t(grid);
-        if (ws.partial.n < need) ws.partial.alloc(need);
-        b.partial = ws.partial.p;
-        b.zzcta = ws.partial.p + size_t(grid) * MNW * MNU * 8 * 64;
-        if (dw) gram_midb_kernel<true><<<grid, MNT, smem, st>>>(b);
-        else gram_midb_kernel<false><<<grid, MNT, smem, st>>>(b);
-        FRK_CUDA(cudaGetLastError());
-        MidArgs ra{};
-        ra.K = K; ra.T = T; ra.nsets = b.nsets; ra.partial = b.partial; ra.zzcta = b.zzcta;
-        gram_mid_reduce_kernel<<<b.ntiles, 256, 0, st>>>(ra, dtiles, grid, dpacked);
-        FRK_CUDA(cudaGetLastError());
-        ws.last_nsplit = grid;
-        ws.last_npairs = 1;
-        return true;
-    }
     MidArgs a;
     a.K = K; a.T = T; a.n = n; a.w = dw;
     a.kb = ws.mid_kb;

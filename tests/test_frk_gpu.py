@@ -416,7 +416,7 @@ def _frk_error():
     return FrkError
 
 
-@pytest.mark.parametrize("path", ["", "mid:tensor", "mid:cpasync", "narrow", "tma", "cpasync"])
+@pytest.mark.parametrize("path", ["mid", "narrow", "tma", "cpasync"])
 @pytest.mark.parametrize("n,K,T,weighted", [(100_003, 32, 4, False), (50_000, 5, 1, True), (77_777, 48, 8, False),
                                              (20_001, 17, 0, False), (64_000, 40, 16, True), (999, 3, 2, False),
                                              (70_001, 64, 4, False), (33_333, 100, 1, True), (41_000, 128, 16, False),
@@ -430,12 +430,7 @@ def test_gram_small_K_variants(n, K, T, weighted, path, monkeypatch):
     import torch
     from autofrk_b200 import _lib
 
-    monkeypatch.delenv("FRK_GRAM_PATH", raising=False)
-    monkeypatch.delenv("FRK_GRAM_MID_STAGING", raising=False)
-    if path.startswith("mid:"):      # the register-resident kernel with either staging mode (2-D TMA boxes / cp.async)
-        monkeypatch.setenv("FRK_GRAM_MID_STAGING", path[4:])
-    elif path:
-        monkeypatch.setenv("FRK_GRAM_PATH", path)
+    monkeypatch.setenv("FRK_GRAM_PATH", path)
 
     g = torch.Generator(device="cuda").manual_seed(n)
     ld = n + (n & 1)

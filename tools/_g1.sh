@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_frk_gpu.py -q -x -k "gram" > gpurun_out/r2_t4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t4.log
+python -m pytest tests -q -m gpu > gpurun_out/r2_t7.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t7.log
 python tools/gram_probe.py > gpurun_out/r2_gram_probe.log 2>&1
-cp gpurun_out/gram_probe.json gpurun_out/gram_probe_r02_v4.json
-REPS=1 ncu --set full --import-source on --clock-control none -k regex:gram_midb_kernel -c 3 -f -o gpurun_out/gram_mid_r02_v4 python tools/gram_ncu.py 5000000,32,4 5000000,64,4 5000000,100,1 > gpurun_out/r2_ncu_mid.log 2>&1
-tail -5 gpurun_out/r2_t4.log; grep -v '"K": [2-9][0-9][0-9]\|"K": 1000' gpurun_out/r2_gram_probe.log | cut -c1-150
+cp gpurun_out/gram_probe.json gpurun_out/gram_probe_r02_v7.json
+tail -8 gpurun_out/r2_t7.log; grep -v '"K": [2-9][0-9][0-9]\|"K": 1000' gpurun_out/r2_gram_probe.log | cut -c1-130

@@ -29,12 +29,22 @@ def main():
     z_all = torch.randn((T, n), dtype=torch.float64, device="cuda", generator=g)
     r0, r1 = D.shard_rows(n, world, rank)
     x, Z = x_all[:, r0:r1].contiguous().T, z_all[:, r0:r1].contiguous().T
-    out = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True)
+    out = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True)          # the collective as one NCCL all-reduce
     res = {}
-    peer_ok, peer_err = None, ""
+    peer_ok, peer_err, packed_diff = None, "", None
     try:   # the same collective as our own kernel over NVLink peer memory
         from autofrk_b200 import _lib
         peer = D.PeerAllReduce(_lib.lib.frk_gram_packed_len(K, T), x.device)
+        # the packed statistics themselves: peer-memory sum against NCCL's all-reduce of the same per-rank buffers
+        D.predict_gram_shard(plan, x, Z, out=peer.buf)
+        nccl_sum = peer.buf.clone()
+        dist.all_reduce(nccl_sum, op=dist.ReduceOp.SUM)
+        peer_sum = peer().clone()
+        packed_diff = float((peer_sum - nccl_sum).abs().max() / nccl_sum.abs().max())
+        ref_sum = peer_sum.clone()
+        dist.broadcast(ref_sum, src=0)
+        packed_bitwise = torch.tensor([int(torch.equal(ref_sum, peer_sum))], device="cuda")
+        dist.all_reduce(packed_bitwise, op=dist.ReduceOp.MIN)
         outp = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True, peer=peer)
         outp2 = D.fit_sharded(plan, x, Z, n_total=n, s=0.0, wSave=True, peer=peer)      # buffer reuse
         relp = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
@@ -44,7 +54,7 @@ def main():
         chk = torch.tensor(np.ascontiguousarray(outp["M"])).cuda()
         ref0 = chk.clone()
         dist.broadcast(ref0, src=0)
-        peer_ok = peer_ok and bool(torch.equal(chk, ref0))
+        peer_ok = peer_ok and bool(torch.equal(chk, ref0)) and bool(packed_bitwise.item() == 1) and packed_diff < 1e-13
     except Exception as e:  # pragma: no cover
         peer_err = repr(e)[:300]
     if rank == 0:
@@ -59,8 +69,11 @@ def main():
         res = dict(world=world, v=[out["v"], ref["v"]], dM=rel(out["M"], ref["M"]), dw=rel(out["w"], ref["w"]),
                    dV=rel(out["V"], ref["V"]), dnll=abs(out["negloglik"] - ref["negloglik"]) / abs(ref["negloglik"]))
         res["ok"] = bool(res["dM"] < 1e-10 and res["dw"] < 1e-10 and res["dV"] < 1e-10 and res["dnll"] < 1e-12)
+        res["collective_nccl_vs_single_gpu"] = "ok" if res["ok"] else "MISMATCH"
         res["peer_allreduce_ok"] = peer_ok
+        res["peer_vs_nccl_packed_max_rel_diff"] = packed_diff
         res["peer_err"] = peer_err
+        res["ok"] = bool(res["ok"] and peer_ok is not False)
         print(json.dumps(res))
     dist.barrier()
     dist.destroy_process_group()

@@ -12,10 +12,7 @@ from autofrk_b200 import _lib
 def run(n, K, T, reps=3, path=""):
     import os
     os.environ.pop("FRK_GRAM_PATH", None)
-    os.environ.pop("FRK_GRAM_MID_STAGING", None)
-    if path.startswith("mid:"):
-        os.environ["FRK_GRAM_MID_STAGING"] = path[4:]
-    elif path:
+    if path:
         os.environ["FRK_GRAM_PATH"] = path
     F = torch.randn((K, n), dtype=torch.float64, device="cuda").T
     Z = torch.randn((max(T, 1), n), dtype=torch.float64, device="cuda").T
@@ -43,10 +40,9 @@ if __name__ == "__main__":
     out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(1_000_000, 1000, 100),
            run(5_000_000, 200, 20), run(5_000_000, 256, 1), run(2_000_000, 446, 1)]
     # shapes default autoFRK() selects (K = 18 ... ~130): the register-resident kernel against the ones it replaces
-    for K, T in ((16, 1), (32, 4), (48, 8), (64, 4), (64, 1), (100, 1), (128, 4), (128, 16), (100, 20)):
+    for K, T in ((8, 1), (16, 1), (24, 1), (32, 4), (48, 8), (64, 4), (64, 1), (100, 1), (128, 4), (128, 16), (100, 20)):
         out.append(run(5_000_000, K, T))
-        out.append(run(5_000_000, K, T, path="mid:tensor"))
-        out.append(run(5_000_000, K, T, path="mid:cpasync"))
+        out.append(run(5_000_000, K, T, path="mid"))
         if K <= 48 and T <= 16:
             out.append(run(5_000_000, K, T, path="narrow"))
         out.append(run(5_000_000, K, T, path="tma"))
