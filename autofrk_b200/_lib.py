@@ -43,6 +43,7 @@ _SIGNATURES = {
     "frk_device_count": (_i32, [C.POINTER(_i32)]),
     "frk_set_device": (_i32, [_i32]),
     "frk_release_cached_memory": (_i32, []),
+    "frk_measure_dmma_peak": (_i32, [_i32, C.POINTER(C.c_double)]),
     "frk_mrtsrcpp_predict": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _vp, _i64, _i64, _vp, _i64, _i64,
                                     _vp, _i64, _i32, _vp]),
     "frk_mrtsrcpp": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

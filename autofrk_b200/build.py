@@ -21,6 +21,12 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    # stream 0 in this library = the calling host thread's own default stream: the K x K stages (launches without a
+    # stream argument, blocking copies) of two host threads do not serialise on the legacy null stream
+    "--default-stream", "per-thread",
+    # stream 0 in this library = the calling host thread's own default stream: the K x K stages (launches without a
+    # stream argument, blocking copies) of two host threads do not serialise on the legacy null stream
+    "--default-stream", "per-thread",
     "-Xcompiler", "-fPIC",
 ]
 LINK_LIBS = ["-lcusolver", "-lcublas"]

@@ -1,6 +1,10 @@
 // C ABI (include/frk_b200.h).  No exception crosses this boundary: everything is converted to
 // (status, thread-local message) -- the C analogue of BEGIN_RCPP/END_RCPP (src/RcppExports.cpp:18,24).
+#include <cstdlib>
+#include <cstring>
 #include <map>
+#include <thread>
+#include <vector>
 #include "capi_internal.cuh"
 
 namespace frk_capi {
@@ -75,6 +79,42 @@ frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, 
     return plan;
 }
 
+// R hands `.Call` pageable REALSXP buffers.  A device -> host copy into pageable memory goes through the driver's own
+// staging buffer and blocks the calling thread: 11.9 GB/s on this pool's boxes against 50 GB/s into pinned memory
+// (profiles/e2e_probe_r02.json).  Page-locking the caller's buffer for the call (cudaHostRegister) pins at ~27 GB/s and
+// ends at 17 GB/s overall.  So large results for pageable destinations are staged: the chunk comes down into one of two
+// pinned buffers owned by the plan at the PCIe rate while a few host threads scatter the previous chunk's columns into
+// the caller's matrix (measured: 25.7 GB/s with 4 threads, 31 GB/s with 8).  FRK_HOST_STAGING=0 turns it off;
+// FRK_HOST_COPY_THREADS sets the thread count.
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+struct ScatterJob {   // columns of one staged chunk (rows x k, dense) -> out[r0 .. r0 + rows, :] with leading dimension ldo
+    std::vector<std::thread> threads;
+    void start(const double* stage, int64_t rows, int k, double* out, int64_t ldo, int nthreads) {
+        join();
+        nthreads = std::max(1, std::min(nthreads, k));
+        for (int tix = 0; tix < nthreads; ++tix) {
+            const int c0 = int(int64_t(k) * tix / nthreads), c1 = int(int64_t(k) * (tix + 1) / nthreads);
+            threads.emplace_back([=] {
+                for (int c = c0; c < c1; ++c)
+                    std::memcpy(out + int64_t(c) * ldo, stage + int64_t(c) * rows, sizeof(double) * size_t(rows));
+            });
+        }
+    }
+    void join() {
+        for (std::thread& t : threads) t.join();
+        threads.clear();
+    }
+    ~ScatterJob() { join(); }
+};
+
 void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, int32_t mode) {
     if (mode != FRK_OUT_X1 && mode != FRK_OUT_BASIS) frk::fail(FRK_EINVAL, "unknown out_mode %d", mode);
     if (n2 <= 0) return;
@@ -111,18 +151,57 @@ void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, i
             frk::plan_predict_basis_dev(mp, plan->dx.p + r0, rows, n2, plan->dbuf[b].p, rc, plan->s_comp);
         FRK_CUDA(cudaEventRecord(plan->ev_comp[b], plan->s_comp));
     };
+    static const int staging_env = [] {
+        const char* e = std::getenv("FRK_HOST_STAGING");
+        return e ? std::atoi(e) : 1;
+    }();
+    static const int copy_threads = [] {   // default: the host cores divided among the visible GPUs (one process each), 2..8
+        if (const char* e = std::getenv("FRK_HOST_COPY_THREADS")) return std::max(1, std::atoi(e));
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 1; }
+        const int hw = int(std::thread::hardware_concurrency());
+        return std::max(2, std::min(8, hw / std::max(1, ndev)));
+    }();
+    const bool staged = staging_env != 0 && sizeof(double) * size_t(n2) * size_t(k) >= (size_t(64) << 20) &&
+                        !host_pointer_is_pinned(out);
+    if (staged && plan->hstage_doubles < size_t(rc) * k) {
+        for (int b = 0; b < 2; ++b) {
+            if (plan->hstage[b]) cudaFreeHost(plan->hstage[b]);
+            plan->hstage[b] = nullptr;
+            FRK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&plan->hstage[b]), sizeof(double) * size_t(rc) * k, cudaHostAllocDefault));
+        }
+        plan->hstage_doubles = size_t(rc) * k;
+    }
+    ScatterJob scatter[2];
     compute(0);
     for (int c = 0; c < nchunk; ++c) {
         const int b = c & 1;
         const int64_t r0 = starts[c], rows = starts[c + 1] - r0;
         if (c + 1 < nchunk) compute(c + 1);
         FRK_CUDA(cudaStreamWaitEvent(plan->s_copy, plan->ev_comp[b], 0));
-        FRK_CUDA(cudaMemcpy2DAsync(out + r0, sizeof(double) * n2, plan->dbuf[b].p, sizeof(double) * rc,
-                                   sizeof(double) * rows, size_t(k), cudaMemcpyDeviceToHost, plan->s_copy));
-        FRK_CUDA(cudaEventRecord(plan->ev_copy[b], plan->s_copy));
+        if (staged) {
+            scatter[b].join();                                   // chunk c-2 has left this staging buffer
+            FRK_CUDA(cudaMemcpy2DAsync(plan->hstage[b], sizeof(double) * rows, plan->dbuf[b].p, sizeof(double) * rc,
+                                       sizeof(double) * rows, size_t(k), cudaMemcpyDeviceToHost, plan->s_copy));
+            FRK_CUDA(cudaEventRecord(plan->ev_copy[b], plan->s_copy));
+            if (c >= 1) {                                        // while chunk c comes down, scatter chunk c-1
+                FRK_CUDA(cudaEventSynchronize(plan->ev_copy[b ^ 1]));
+                scatter[b ^ 1].start(plan->hstage[b ^ 1], starts[c] - starts[c - 1], k, out + starts[c - 1], n2, copy_threads);
+            }
+        } else {
+            FRK_CUDA(cudaMemcpy2DAsync(out + r0, sizeof(double) * n2, plan->dbuf[b].p, sizeof(double) * rc,
+                                       sizeof(double) * rows, size_t(k), cudaMemcpyDeviceToHost, plan->s_copy));
+            FRK_CUDA(cudaEventRecord(plan->ev_copy[b], plan->s_copy));
+        }
     }
     FRK_CUDA(cudaStreamSynchronize(plan->s_comp));
     FRK_CUDA(cudaStreamSynchronize(plan->s_copy));
+    if (staged) {
+        const int c = nchunk - 1;
+        scatter[c & 1].start(plan->hstage[c & 1], starts[c + 1] - starts[c], k, out + starts[c], n2, copy_threads);
+        scatter[0].join();
+        scatter[1].join();
+    }
 }
 
 }  // namespace frk_capi

@@ -1,5 +1,6 @@
 // C ABI, part 2: fixed-rank-kriging reductions (K4, K5) and the fused predict -> reduce paths.
 #include "capi_internal.cuh"
+#include "panel_gemm.cuh"
 
 using frk_capi::guarded;
 using frk_capi::require_device;
@@ -17,16 +18,6 @@ __global__ void axpy_kernel(double* __restrict__ acc, const double* __restrict__
     if (i < len) acc[i] = first ? x[i] : acc[i] + x[i];
 }
 
-// se[i] = sqrt(max(0, sum_j FV[i,j] * F[i,j]))     R/autoFRK.R:1220
-__global__ void rowdot_sqrt_kernel(const double* __restrict__ FV, const double* __restrict__ F, int64_t rows,
-                                   int64_t ld, int K, double* __restrict__ se) {
-    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (i >= rows) return;
-    double s = 0.0;
-    for (int j = 0; j < K; ++j) s = fma(FV[i + int64_t(j) * ld], F[i + int64_t(j) * ld], s);
-    se[i] = sqrt(fmax(0.0, s));
-}
-
 // se[i] = sqrt(max(0, sum_j sgn[j] * Y[i,j]^2)): rowSums((basis V) * basis) with V = R diag(sgn) R', Y = basis R
 __global__ void signed_rownorm_kernel(const double* __restrict__ Y, int64_t rows, int64_t ld, int r,
                                       const double* __restrict__ sgn, double* __restrict__ se) {
@@ -40,10 +31,68 @@ __global__ void signed_rownorm_kernel(const double* __restrict__ Y, int64_t rows
     se[i] = sqrt(fmax(0.0, s));
 }
 
+// lower triangle <- (A + A')/2
+__global__ void symmetrize_lower_kernel(double* __restrict__ A, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        for (int j = blockIdx.y; j < i; j += gridDim.y) A[i + int64_t(j) * n] = 0.5 * (A[i + int64_t(j) * n] + A[j + int64_t(i) * n]);
+}
+
 __global__ void scale_cols_inplace_kernel(double* __restrict__ A, int n, int cols, const double* __restrict__ f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i < n && j < cols) A[i + int64_t(j) * n] *= f[j];
+}
+
+// B = [w | R] on the device with V = R diag(sgn) R' (eigen-decomposition of V; |lambda| <= K eps max|lambda| dropped --
+// the rank tolerance of LAPACK-style rank tests and the size of the rounding error of the reference's own FP64
+// evaluation of the bilinear form), so that
+//   yhat = basis %*% w                                                              R/autoFRK.R:1216
+//   se^2 = rowSums((basis %*% V) * basis) = sum_j sgn_j (basis %*% R)[, j]^2        R/autoFRK.R:1220
+// both come out of ONE product basis %*% B with q = T + rank(V) columns.  V from cMLEimat has rank <= min(K, T).
+// Returns rank(V) (0 when V == nullptr).
+int coefficient_matrix_dev(const double* w, int T, const double* V, int K, cudaStream_t st, frk::DevBuf<double>& dB,
+                           std::vector<double>& sgn) {
+    int r = 0;
+    sgn.clear();
+    if (V) {
+        frk::DevBuf<double> dV(size_t(K) * K), lam(static_cast<size_t>(K));
+        FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+        // b' V b = b' ((V + V')/2) b: a V that is symmetric only up to rounding (the kriging V = M - ... is) must enter
+        // through its symmetric part, or the eigen-solver's lower triangle would stand for a different quadratic form
+        symmetrize_lower_kernel<<<dim3(unsigned((K + 127) / 128), unsigned(std::min(K, 65535))), 128, 0, st>>>(dV.p, K);
+        FRK_CUDA(cudaGetLastError());
+        FRK_CUDA(cudaStreamSynchronize(st));
+        frk::sym_eigen_dev(dV.p, K, lam.p);                     // ascending; lower triangle of V is read
+        std::vector<double> lam_h(K);
+        FRK_CUDA(cudaMemcpy(lam_h.data(), lam.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
+        double amax = 0.0;
+        for (double l : lam_h) amax = std::fmax(amax, std::fabs(l));
+        std::vector<int> keep;
+        for (int i = K - 1; i >= 0; --i)
+            if (std::fabs(lam_h[i]) > double(K) * 2.220446049250313e-16 * amax) keep.push_back(i);
+        r = int(keep.size());
+        dB.alloc(size_t(K) * (T + std::max(r, 1)));
+        std::vector<double> scale(std::max(r, 1));
+        for (int j = 0; j < r; ++j) {
+            scale[j] = std::sqrt(std::fabs(lam_h[keep[j]]));
+            sgn.push_back(lam_h[keep[j]] < 0.0 ? -1.0 : 1.0);
+            FRK_CUDA(cudaMemcpyAsync(dB.p + size_t(K) * (T + j), dV.p + size_t(K) * keep[j], sizeof(double) * K,
+                                     cudaMemcpyDeviceToDevice, st));
+        }
+        if (r > 0) {
+            frk::DevBuf<double> dscale(static_cast<size_t>(r));
+            FRK_CUDA(cudaMemcpyAsync(dscale.p, scale.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
+            dim3 grid(unsigned((K + 127) / 128), unsigned(r));
+            scale_cols_inplace_kernel<<<grid, 128, 0, st>>>(dB.p + size_t(K) * T, K, r, dscale.p);
+            FRK_CUDA(cudaGetLastError());
+            FRK_CUDA(cudaStreamSynchronize(st));
+        }
+    } else {
+        dB.alloc(size_t(K) * T);
+    }
+    FRK_CUDA(cudaMemcpyAsync(dB.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice, st));
+    return r;
 }
 
 // One-shot all-reduce over NVLink peer memory: every rank reads every rank's packed statistics straight from the
@@ -310,18 +359,15 @@ int32_t frk_cMLE(const double* Fk, int64_t n, int32_t K, int32_t TT, double trS,
         if (M) FRK_CUDA(cudaMemcpy(M, out.M.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
         if (nL) *nL = wsave ? out.nL : 0;
         if (wsave && Fk && L) {
-            // L = Fk %*% LA[, 1:nL]   (R/autoFRK.R:387-391), a plain library GEMM streamed over row chunks
-            frk::LinalgHandles& lh = frk::linalg_handles();
-            FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
-            const int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
+            // L = Fk %*% LA[, 1:nL]   (R/autoFRK.R:387-391): the panel kernel, streamed over row chunks
+            int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
+            rc += rc & 1;
             frk::DevBuf<double> dF(size_t(rc) * K), dL(size_t(rc) * out.nL);
-            const double one = 1.0, zero = 0.0;
             for (int64_t r0 = 0; r0 < n; r0 += rc) {
                 const int64_t rows = std::min(rc, n - r0);
                 FRK_CUDA(cudaMemcpy2D(dF.p, sizeof(double) * rc, Fk + r0, sizeof(double) * n, sizeof(double) * rows,
                                       size_t(K), cudaMemcpyHostToDevice));
-                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), out.nL, K, &one, dF.p, int(rc),
-                                       out.LA.p, K, &zero, dL.p, int(rc)));
+                frk::panel_times_small_dev(dF.p, rows, rc, K, out.LA.p, K, out.nL, dL.p, rc, nullptr);
                 FRK_CUDA(cudaMemcpy2D(L + r0, sizeof(double) * n, dL.p, sizeof(double) * rc, sizeof(double) * rows,
                                       size_t(out.nL), cudaMemcpyDeviceToHost));
             }
@@ -339,49 +385,11 @@ int32_t frk_plan_predict_frk(frk_plan* plan, const double* xnew, int64_t n2, con
         if (T < 1 || !w || !yhat) frk::fail(FRK_EINVAL, "w (K x T) and yhat (n2 x T) are required");
         cudaStream_t st = nullptr;
         const bool want_se = (V != nullptr && se != nullptr);
-        // Coefficient matrix B = [w | R] with V = R diag(sgn) R' (eigen-decomposition of V; |lambda| <= K eps max|lambda|
-        // dropped -- the rank tolerance of LAPACK-style rank tests and the size of the rounding error of the
-        // reference's own FP64 evaluation of the bilinear form).  Then
-        //   yhat = basis %*% w                                   R/autoFRK.R:1216
-        //   se^2 = rowSums((basis %*% V) * basis) = sum_j sgn_j (basis %*% R)[, j]^2   R/autoFRK.R:1220
-        // and basis %*% B comes straight out of K1 through a derived plan (W' = W B_rest): q = T + rank(V) columns
-        // of tensor work instead of K columns plus an n2 x K x K product, and no n2 x K basis anywhere.
-        // V from cMLEimat has rank <= min(K, T).
+        // B = [w | R] (coefficient_matrix_dev): basis %*% B comes straight out of K1 through a derived plan (W' = W B_rest):
+        // q = T + rank(V) columns of tensor work instead of K columns plus an n2 x K x K product, and no n2 x K basis anywhere.
         std::vector<double> sgn;
         frk::DevBuf<double> dB;
-        int r = 0;
-        if (want_se) {
-            frk::DevBuf<double> dV(size_t(K) * K), lam(static_cast<size_t>(K));
-            FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
-            frk::sym_eigen_dev(dV.p, K, lam.p);                     // ascending; lower triangle of V is read
-            std::vector<double> lam_h(K);
-            FRK_CUDA(cudaMemcpy(lam_h.data(), lam.p, sizeof(double) * K, cudaMemcpyDeviceToHost));
-            double amax = 0.0;
-            for (double l : lam_h) amax = std::fmax(amax, std::fabs(l));
-            std::vector<int> keep;
-            for (int i = K - 1; i >= 0; --i)
-                if (std::fabs(lam_h[i]) > double(K) * 2.220446049250313e-16 * amax) keep.push_back(i);
-            r = int(keep.size());
-            dB.alloc(size_t(K) * (T + std::max(r, 1)));
-            std::vector<double> scale(std::max(r, 1));
-            for (int j = 0; j < r; ++j) {
-                scale[j] = std::sqrt(std::fabs(lam_h[keep[j]]));
-                sgn.push_back(lam_h[keep[j]] < 0.0 ? -1.0 : 1.0);
-                FRK_CUDA(cudaMemcpyAsync(dB.p + size_t(K) * (T + j), dV.p + size_t(K) * keep[j], sizeof(double) * K,
-                                         cudaMemcpyDeviceToDevice, st));
-            }
-            if (r > 0) {
-                frk::DevBuf<double> dscale(static_cast<size_t>(r));
-                FRK_CUDA(cudaMemcpyAsync(dscale.p, scale.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
-                dim3 grid(unsigned((K + 127) / 128), unsigned(r));
-                scale_cols_inplace_kernel<<<grid, 128, 0, st>>>(dB.p + size_t(K) * T, K, r, dscale.p);
-                FRK_CUDA(cudaGetLastError());
-                FRK_CUDA(cudaStreamSynchronize(st));
-            }
-        } else {
-            dB.alloc(size_t(K) * T);
-        }
-        FRK_CUDA(cudaMemcpyAsync(dB.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice, st));
+        const int r = coefficient_matrix_dev(w, T, want_se ? V : nullptr, K, st, dB, sgn);
         const int q = T + r;
         struct PlanGuard {
             frk::MrtsPlan* p;
@@ -473,32 +481,31 @@ int32_t frk_basis_predict_frk(const double* F, int64_t n, int32_t K, const doubl
         require_device();
         if (n <= 0) return;
         if (K < 1 || T < 1 || !F || !w || !yhat) frk::fail(FRK_EINVAL, "F (n x K), w (K x T) and yhat (n x T) are required");
-        frk::LinalgHandles& lh = frk::linalg_handles();
         cudaStream_t st = nullptr;
-        FRK_CUBLAS(cublasSetStream(lh.blas, st));
-        const int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
         const bool want_se = (V != nullptr && se != nullptr);
-        frk::DevBuf<double> dF(size_t(rc) * K), dw(size_t(K) * T), dy(size_t(rc) * T), dV, dFV, dse;
-        FRK_CUDA(cudaMemcpy(dw.p, w, sizeof(double) * K * T, cudaMemcpyHostToDevice));
+        // one product basis %*% [w | R] per row chunk (panel kernel) instead of basis %*% w plus the n x K x K product
+        // basis %*% V: q = T + rank(V) columns
+        std::vector<double> sgn;
+        frk::DevBuf<double> dB;
+        const int r = coefficient_matrix_dev(w, T, want_se ? V : nullptr, K, st, dB, sgn);
+        const int q = T + r;
+        int64_t rc = std::min<int64_t>(n, std::max<int64_t>(1024, (int64_t(512) << 20) / (int64_t(K) * 8)));
+        rc += rc & 1;
+        frk::DevBuf<double> dF(size_t(rc) * K), dy(size_t(rc) * q), dse, dsgn;
         if (want_se) {
-            dV.alloc(size_t(K) * K);
-            dFV.alloc(size_t(rc) * K);
             dse.alloc(static_cast<size_t>(rc));
-            FRK_CUDA(cudaMemcpy(dV.p, V, sizeof(double) * K * K, cudaMemcpyHostToDevice));
+            dsgn.alloc(static_cast<size_t>(std::max(r, 1)));
+            if (r > 0) FRK_CUDA(cudaMemcpyAsync(dsgn.p, sgn.data(), sizeof(double) * r, cudaMemcpyHostToDevice, st));
         }
-        const double one = 1.0, zero = 0.0;
         for (int64_t r0 = 0; r0 < n; r0 += rc) {
             const int64_t rows = std::min(rc, n - r0);
             FRK_CUDA(cudaMemcpy2DAsync(dF.p, sizeof(double) * rc, F + r0, sizeof(double) * n, sizeof(double) * rows,
                                        size_t(K), cudaMemcpyHostToDevice, st));
-            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), T, K, &one, dF.p, int(rc), dw.p, K, &zero,
-                                   dy.p, int(rc)));                        // R/autoFRK.R:1216
+            frk::panel_times_small_dev(dF.p, rows, rc, K, dB.p, K, q, dy.p, rc, st);            // R/autoFRK.R:1216,1220
             FRK_CUDA(cudaMemcpy2DAsync(yhat + r0, sizeof(double) * n, dy.p, sizeof(double) * rc, sizeof(double) * rows,
                                        size_t(T), cudaMemcpyDeviceToHost, st));
-            if (want_se) {                                                  // R/autoFRK.R:1220
-                FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), K, K, &one, dF.p, int(rc), dV.p, K,
-                                       &zero, dFV.p, int(rc)));
-                rowdot_sqrt_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dFV.p, dF.p, rows, rc, K, dse.p);
+            if (want_se) {
+                signed_rownorm_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(dy.p + size_t(rc) * T, rows, rc, r, dsgn.p, dse.p);
                 FRK_CUDA(cudaGetLastError());
                 FRK_CUDA(cudaMemcpyAsync(se + r0, dse.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
             }

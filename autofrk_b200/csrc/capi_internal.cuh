@@ -46,6 +46,9 @@ struct frk_plan {
     cudaStream_t s_comp = nullptr, s_copy = nullptr;
     cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     frk::DevBuf<double> dx, dbuf[2];
+    // pinned staging of results that go to pageable host memory (two chunks; see predict_host)
+    double* hstage[2] = {nullptr, nullptr};
+    size_t hstage_doubles = 0;
     // fused predict -> Gram / predict -> kriging: one basis chunk + packed partial statistics
     frk::DevBuf<double> fchunk, packed_tmp, ytmp;
     ~frk_plan() {
@@ -53,6 +56,8 @@ struct frk_plan {
             if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
             if (ev_copy[i]) cudaEventDestroy(ev_copy[i]);
         }
+        for (int i = 0; i < 2; ++i)
+            if (hstage[i]) cudaFreeHost(hstage[i]);
         if (s_comp) cudaStreamDestroy(s_comp);
         if (s_copy) cudaStreamDestroy(s_copy);
         if (mp) frk::plan_destroy(mp);

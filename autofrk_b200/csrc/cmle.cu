@@ -9,6 +9,7 @@
 // (checked against the literal sequence in tests/test_oracle.py).  The two eigensolves are cuSOLVER
 // syevd, the K x K products plain cuBLAS GEMMs; the O(K) scalar rule for v (sol.v, :335-351) runs on
 // the host on the K eigenvalues.
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <vector>
@@ -23,21 +24,21 @@ namespace {
 __global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, int rows, int cols,
                                   double* __restrict__ dst, int64_t ldd) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i < rows && j < cols) dst[i + int64_t(j) * ldd] = src[i + int64_t(j) * lds];
+    if (i < rows)
+        for (int j = blockIdx.y; j < cols; j += gridDim.y) dst[i + int64_t(j) * ldd] = src[i + int64_t(j) * lds];
 }
 
 // B[:, j] = A[:, j] * f(j)
 __global__ void scale_cols_kernel(const double* __restrict__ A, int n, int cols, const double* __restrict__ f,
                                   double* __restrict__ B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i < n && j < cols) B[i + int64_t(j) * n] = A[i + int64_t(j) * n] * f[j];
+    if (i < n)
+        for (int j = blockIdx.y; j < cols; j += gridDim.y) B[i + int64_t(j) * n] = A[i + int64_t(j) * n] * f[j];
 }
 __global__ void scale_rows_kernel(double* __restrict__ A, int n, int cols, const double* __restrict__ f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i < n && j < cols) A[i + int64_t(j) * n] *= f[i];
+    if (i < n)
+        for (int j = blockIdx.y; j < cols; j += gridDim.y) A[i + int64_t(j) * n] *= f[i];
 }
 // R/helper.R:22-24: sroot = sqrt(pmax(value,0)); sroot[sroot==0] = Inf; 1/sroot
 __global__ void inv_sqrt_kernel(const double* __restrict__ lam, int n, double* __restrict__ out) {
@@ -48,13 +49,14 @@ __global__ void inv_sqrt_kernel(const double* __restrict__ lam, int n, double* _
 }
 __global__ void mirror_lower_kernel(double* __restrict__ A, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (i < n && j < n && i > j) A[j + int64_t(i) * n] = A[i + int64_t(j) * n];
+    if (i < n)
+        for (int j = blockIdx.y; j < n; j += gridDim.y)
+            if (i > j) A[j + int64_t(i) * n] = A[i + int64_t(j) * n];
 }
 
 void launch2d(int rows, int cols, dim3& grid, dim3& block) {
     block = dim3(128);
-    grid = dim3(unsigned((rows + 127) / 128), unsigned(cols));
+    grid = dim3(unsigned((rows + 127) / 128), unsigned(std::min(cols, 65535)));   // the kernels stride over columns in y
 }
 
 }  // namespace
@@ -100,7 +102,7 @@ double neg2llik(const std::vector<double>& d, double s, double v, double trS, do
 
 void half_from_gram_dev(const double* dG, int64_t ldg, int K, double* dhalf) {
     LinalgHandles& lh = linalg_handles();
-    FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
+    FRK_CUBLAS(cublasSetStream(lh.blas, cudaStreamPerThread));
     DevBuf<double> U(size_t(K) * K), Us(size_t(K) * K), lam(static_cast<size_t>(K)), inv(static_cast<size_t>(K));
     dim3 grid, block;
     launch2d(K, K, grid, block);
@@ -118,7 +120,7 @@ void cmle_core_dev(const double* dhalf, double* dJSJ /* K x K, lower triangle va
                    int64_t ldc, int K, int T, double n, double trS, double s, double ldet, bool wsave, bool only_loglik,
                    bool has_vfixed, double vfixed, CmleOut& out, const std::vector<double>* eigen_asc) {
     LinalgHandles& lh = linalg_handles();
-    FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
+    FRK_CUBLAS(cublasSetStream(lh.blas, cudaStreamPerThread));
     const double one = 1.0, zero = 0.0;
     std::vector<double> asc(K), d(K);
     if (eigen_asc) {                                                // dJSJ already holds P (ascending), see below
@@ -160,7 +162,7 @@ void cmle_core_dev(const double* dhalf, double* dJSJ /* K x K, lower triangle va
     mirror_lower_kernel<<<grid, block>>>(out.M.p, K);
     FRK_CUDA(cudaGetLastError());
     if (!wsave) {
-        FRK_CUDA(cudaDeviceSynchronize());
+        FRK_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
         return;
     }
     // LA = half P diag(sqrt(dhat)) in R's descending column order: L = Fk %*% LA[, dhat > 0]   :387-391
@@ -172,7 +174,7 @@ void cmle_core_dev(const double* dhalf, double* dJSJ /* K x K, lower triangle va
         for (int c = 0; c < K; ++c)  // tmp holds hP diag(sq) in ascending order: reverse the columns
             FRK_CUDA(cudaMemcpyAsync(out.LA.p + size_t(c) * K, tmp.p + size_t(K - 1 - c) * K, sizeof(double) * K,
                                      cudaMemcpyDeviceToDevice, nullptr));
-        FRK_CUDA(cudaDeviceSynchronize());
+        FRK_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
     }
     // V = hP diag(dhat (s+v)/(s+v+dhat)) hP'                         closed form of :470-474
     FRK_CUDA(cudaMemcpy(coef.p, cv.data(), sizeof(double) * K, cudaMemcpyHostToDevice));
@@ -192,14 +194,14 @@ void cmle_core_dev(const double* dhalf, double* dJSJ /* K x K, lower triangle va
         FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, K, T, K, &one, hP.p, K, pc.p, K, &zero, out.w.p, K));
     }
     FRK_CUDA(cudaGetLastError());
-    FRK_CUDA(cudaDeviceSynchronize());
+    FRK_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
 }
 
 void cmle_imat_from_stats_dev(const double* dG, int64_t ldg, const double* dC, int64_t ldc, double zz, int K, int T,
                               double n, double s, bool wsave, bool only_loglik, CmleOut& out) {
     if (K < 1 || T < 1) fail(1, "K and T must be positive");
     LinalgHandles& lh = linalg_handles();
-    FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
+    FRK_CUBLAS(cublasSetStream(lh.blas, cudaStreamPerThread));
     const double one = 1.0, zero = 0.0;
     const double trS = zz / T;                                      // R/autoFRK.R:431
     DevBuf<double> half(size_t(K) * K), t(size_t(K) * T), JSJ(size_t(K) * K);
@@ -258,8 +260,8 @@ void negloglik_sweep_dev(const double* dG, int64_t ldg, const double* dC, int64_
     }
     const double nan = std::numeric_limits<double>::quiet_NaN();
     LinalgHandles& lh = linalg_handles();
-    FRK_CUBLAS(cublasSetStream(lh.blas, nullptr));
-    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, nullptr));
+    FRK_CUBLAS(cublasSetStream(lh.blas, cudaStreamPerThread));
+    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, cudaStreamPerThread));
     const double one = 1.0, zero = 0.0;
     const double trS = zz / T;                                       // R/autoFRK.R:431
     DevBuf<double> L(size_t(Kmax) * Kmax), W(size_t(Kmax) * T);

@@ -18,6 +18,7 @@
 //     HBM once and served to the other tile pairs from the 126 MB L2.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "frk_common.cuh"
@@ -335,15 +336,13 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         a.partial = ws.partial.p;
         const bool aligned = (reinterpret_cast<uintptr_t>(dF) % 16 == 0) && (ldf % 2 == 0) &&
                              (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));
-        static bool attr_set_on[64] = {};  // the opt-in to large dynamic shared memory is per device
-        bool& attr_set = attr_set_on[dev & 63];
-        if (!attr_set) {
+        static std::once_flag attr_once[64];  // the opt-in to large dynamic shared memory is per device; thread-safe
+        std::call_once(attr_once[dev & 63], [] {
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
             FRK_CUDA(cudaFuncSetAttribute(gram_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GRAM_SMEM)));
-            attr_set = true;
-        }
+        });
         const int grid = a.nsplit * a.npairs;
         if (aligned && !dw) gram_kernel<true, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);
         else if (!aligned && !dw) gram_kernel<false, false><<<grid, NTHREADS, GRAM_SMEM, st>>>(a);

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <iterator>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 #include <cuda.h>
@@ -583,17 +584,15 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
 
     const CUtensorMap tmF = make_map(dF, n, K, ldf);
     const CUtensorMap tmZ = (T > 0) ? make_map(dZ, n, T, ldz) : tmF;
-    static bool attr_set_on[64] = {};  // the opt-in to large dynamic shared memory is per device
+    static std::once_flag attr_once[64];  // the opt-in to large dynamic shared memory is per device; thread-safe
     int dev = 0;
     FRK_CUDA(cudaGetDevice(&dev));
-    bool& attr_set = attr_set_on[dev & 63];
-    if (!attr_set) {
+    std::call_once(attr_once[dev & 63], [] {
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(16))));
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(16))));
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(32))));
         FRK_CUDA(cudaFuncSetAttribute(gram_tma_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes_for(32))));
-        attr_set = true;
-    }
+    });
     const int grid = std::min(sms, a.nitems);
     if (kr == 16) {
         if (dw) gram_tma_kernel<true, 16><<<grid, NTHREADS, smem_bytes_for(16), st>>>(tmF, tmZ, a);

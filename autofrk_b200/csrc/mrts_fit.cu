@@ -281,7 +281,7 @@ void mrts_fit_dev(const double* hXu, const double* h_xobs_diag, int64_t m, int d
 
 void sym_eigen_dev(double* dA, int n, double* dvalues) {
     LinalgHandles& lh = linalg_handles();
-    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, nullptr));
+    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, cudaStreamPerThread));
     int lwork = 0;
     FRK_CUSOLVER(cusolverDnDsyevd_bufferSize(lh.solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dA, n, dvalues,
                                              &lwork));

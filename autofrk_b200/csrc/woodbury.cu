@@ -6,6 +6,7 @@
 #include <cmath>
 #include <vector>
 #include "capi_internal.cuh"
+#include "panel_gemm.cuh"
 
 using frk_capi::guarded;
 using frk_capi::require_device;
@@ -29,14 +30,14 @@ __global__ void axpy_packed_kernel(double* __restrict__ acc, const double* __res
 __global__ void invcz_finish_kernel(const double* __restrict__ z, const double* __restrict__ LI, const double* __restrict__ ir,
                                     int64_t rows, int64_t ld, int T, double* __restrict__ out) {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int t = blockIdx.y;
-    if (i < rows && t < T) out[i + int64_t(t) * ld] = (z[i + int64_t(t) * ld] - LI[i + int64_t(t) * ld]) * ir[i];
+    if (i < rows)
+        for (int t = blockIdx.y; t < T; t += gridDim.y) out[i + int64_t(t) * ld] = (z[i + int64_t(t) * ld] - LI[i + int64_t(t) * ld]) * ir[i];
 }
 
 // A (K x K, SPD, lower triangle read; destroyed) <- chol; B (K x nrhs) <- A^{-1} B; returns log det A
 double chol_solve_logdet(double* dA, int K, double* dB, int nrhs) {
     frk::LinalgHandles& lh = frk::linalg_handles();
-    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, nullptr));
+    FRK_CUSOLVER(cusolverDnSetStream(lh.solver, cudaStreamPerThread));
     int lwork = 0;
     FRK_CUSOLVER(cusolverDnDpotrf_bufferSize(lh.solver, CUBLAS_FILL_MODE_LOWER, K, dA, K, &lwork));
     frk::DevBuf<double> work(static_cast<size_t>(lwork));
@@ -107,13 +108,11 @@ int32_t frk_invCz(const double* Rdiag, const double* L, const double* z, int64_t
         double* dinner = packed.p + size_t(K) * K;
         chol_solve_logdet(packed.p, K, dinner, T);
         // pass 2: iRZ - iR %*% (L %*% inner)   (:849-851)
-        const double one = 1.0, zero = 0.0;
         for (int64_t r0 = 0; r0 < n; r0 += rc) {
             const int64_t rows = std::min(rc, n - r0);
             if (n > rc) upload(r0, rows);  // single chunk: still resident from pass 1
-            FRK_CUBLAS(cublasDgemm(lh.blas, CUBLAS_OP_N, CUBLAS_OP_N, int(rows), T, K, &one, dL.p, int(rc), dinner, K, &zero,
-                                   dLI.p, int(rc)));
-            dim3 grid(unsigned((rows + 255) / 256), unsigned(T));
+            frk::panel_times_small_dev(dL.p, rows, rc, K, dinner, K, T, dLI.p, rc, st);       // L %*% inner
+            dim3 grid(unsigned((rows + 255) / 256), unsigned(std::min(T, 65535)));
             invcz_finish_kernel<<<grid, 256, 0, st>>>(dz.p, dLI.p, dir.p, rows, rc, T, dout.p);
             FRK_CUDA(cudaGetLastError());
             FRK_CUDA(cudaMemcpy2DAsync(out + r0, sizeof(double) * n, dout.p, sizeof(double) * rc, sizeof(double) * rows,
@@ -287,7 +286,7 @@ int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, co
         int32_t rc = frk_plan_predict_gram_dev(plan, dx.p, n2, ld, T > 0 ? dZ.p : nullptr, T, ld, weights ? dw.p : nullptr,
                                                packed.p, 0, nullptr);
         if (rc != FRK_OK) frk::fail(rc, "%s", frk_last_error());
-        FRK_CUDA(cudaDeviceSynchronize());
+        FRK_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
         FRK_CUDA(cudaMemcpy(G, packed.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
         if (T > 0 && C) FRK_CUDA(cudaMemcpy(C, packed.p + size_t(K) * K, sizeof(double) * K * T, cudaMemcpyDeviceToHost));
         if (zz) FRK_CUDA(cudaMemcpy(zz, packed.p + size_t(K) * K + size_t(K) * T, sizeof(double), cudaMemcpyDeviceToHost));

@@ -14,6 +14,14 @@
  *     host memory on return, as `.Call` requires); `_dev` functions take DEVICE pointers and a
  *     `cudaStream_t` (passed as void*) and are asynchronous on that stream.
  * There is no CPU fallback: without a CUDA device every compute entry point fails with FRK_ECUDA.
+ *
+ * Concurrency: the library is safe to call from several host threads at once (per-thread handles, workspaces and
+ * default stream; a device-memory cache behind a mutex).  Within ONE host thread, and for ONE plan object, calls
+ * must be issued on one stream at a time: the Gram workspace (one per host thread and device) and a plan's chunk
+ * buffers are reused by consecutive calls without cross-stream ordering.  Two streams -> two host threads (and two
+ * plans), or wait for the first call's stream before issuing on the second.
+ * Limits: dimensions are int64_t / int32_t as declared; n2 < 2^31 rows per call for the TMA-staged Gram kernels
+ * (larger inputs take the cp.async kernel); knots m <= 65535 (the reference caps them at maxknot = 5000).
  */
 #ifndef FRK_B200_H
 #define FRK_B200_H
@@ -39,6 +47,10 @@ int32_t frk_device_count(int32_t* count);
 int32_t frk_set_device(int32_t device);
 /* device temporaries are cached between calls; this returns the cached blocks to the driver */
 int32_t frk_release_cached_memory(void);
+/* Measurement aid (no reference counterpart): issue rate of the FP64 tensor instruction every kernel here is built
+ * from (DMMA.8x8x4), in TFLOP/s on the current device: `iters` x 16 dependent-free DMMAs per warp, 16 warps per SM.
+ * bench.py reports it beside the cuBLAS DGEMM figure as the roofline denominator's cross-check. */
+int32_t frk_measure_dmma_peak(int32_t iters, double* tflops);
 
 /* ---------------------------------------------------------------------------------------------
  * Reference boundary, one function per registered `.Call` routine (src/RcppExports.cpp:71-77).

@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -q -m gpu > gpurun_out/r2_t7.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t7.log
-python tools/gram_probe.py > gpurun_out/r2_gram_probe.log 2>&1
-cp gpurun_out/gram_probe.json gpurun_out/gram_probe_r02_v7.json
-tail -8 gpurun_out/r2_t7.log; grep -v '"K": [2-9][0-9][0-9]\|"K": 1000' gpurun_out/r2_gram_probe.log | cut -c1-130
+python -m pytest tests -q -m gpu > gpurun_out/r2_t9.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t9.log
+tail -4 gpurun_out/r2_t9.log
+FRK_HOST_STAGING=0 python tools/e2e_probe.py 1000000 4000000 > gpurun_out/e2e0.log 2>&1; tail -3 gpurun_out/e2e0.log | cut -c1-330
+python tools/e2e_probe.py 1000000 4000000 > gpurun_out/e2e1.log 2>&1; tail -3 gpurun_out/e2e1.log | cut -c1-330
+FRK_HOST_COPY_THREADS=8 python tools/e2e_probe.py 4000000 > gpurun_out/e2e2.log 2>&1; tail -2 gpurun_out/e2e2.log | cut -c1-330
