@@ -7,9 +7,11 @@ device (K4 Gram reductions, K1 basis evaluation) and every K x K eigen-stage in 
   cMLE              R/autoFRK.R:333-397          cMLEimat             R/autoFRK.R:399-480
   selectBasis       R/autoFRK.R:199-331          indeMLE              R/autoFRK.R:739-843
   autoFRK           R/autoFRK.R:121-197          predict_FRK          R/autoFRK.R:1168-1423
-Branches that belong to components SURVEY.md marks out of scope (sparse/non-identity D -> cMLEsp,
-LatticeKrig fine scale -> cMLElk, missing data -> EM0miss / kNN imputation) raise NotImplementedError
-naming the component; nothing silently falls back to host arithmetic.
+The LatticeKrig fine-scale branch (cMLElk, SURVEY.md section 2 #20: out of scope) raises NotImplementedError.  Data with
+NAs run through the masked statistics + EM0miss / kNN imputation entry points built in round 1; the
+one thing such a model cannot do here is `predict_FRK(se_report=True)` -- the per-replicate standard errors of
+R/autoFRK.R:1224-1245 are not implemented and raise NotImplementedError rather than returning a wrong se.
+Nothing falls back to host arithmetic.
 """
 from __future__ import annotations
 
@@ -462,6 +464,10 @@ def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=N
     se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (:1220), both fused behind the basis evaluation."""
     if "w" not in obj:
         raise ValueError('input model (object) should use the option "wsave=TRUE"!')   # :1171-1173
+    if obsloc is not None and obsData is None:
+        # the reference computes yhat only when both are NULL (:1214) or obsData is given (:1248): this call dies there
+        # with "object 'yhat' not found"
+        raise ValueError("obsloc was given without obsData: the reference leaves yhat undefined here (R/autoFRK.R:1214,1248)")
     if newloc is None:
         newloc = obsloc
     G = obj["G"]
@@ -471,12 +477,21 @@ def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=N
         raise ValueError("Basis matrix of new locations should be given (unless the model was fitted with mrts bases)!")
     w = fmat(obj["w"], "w")
     K, TT = w.shape
+    if se_report and obsData is None and obj.get("missing") is not None:
+        # R/autoFRK.R:1224-1245: a model fitted through EM0miss gets one V per replicate (rows observed in that
+        # replicate, pinfo$pick / D, invCz); object$V is NOT the right covariance there
+        raise NotImplementedError("predict_FRK(se_report=True) for a model fitted with missing data (per-replicate "
+                                  "standard errors, R/autoFRK.R:1224-1245) is not implemented")
     V = fmat(obj["V"], "V") if se_report else None
+    if V is not None and V.shape != (K, K):
+        raise ValueError("Dimensions of object$V and object$w are not compatible!")
     se = None
     if basis is None and newloc is not None:
         # basis <- predict.mrts(object$G, newx = newloc) (:1184), fused with the two products on the device
         x = fmat(newloc, "newloc")
         kstar = G.X.shape[1] - G.Xu.shape[1] - 1
+        if G.X.shape[1] != K:                                   # the fused call reads K x T of w and K x K of V
+            raise ValueError("Dimensions of basis and object$w are not compatible!")
         if kstar > 0:
             n2 = x.shape[0]
             yhat = np.empty((n2, TT), order="F")

@@ -7,13 +7,14 @@ metric is quoted on (configs[4]: 100M 2-D locations x 1,000 knots, K=500 on 8 GP
 i.e. 12.5M locations per GPU (weak scaling: N GPUs evaluate N x 12.5M locations).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework
-  python bench.py --impl reference ...                           # the reference's CPU algorithm (oracle port)
+  python bench.py --impl reference ...                           # the reference's CPU path on the host cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -35,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 WORKLOAD = dict(d=2, knots=1000, K=500, rows_per_gpu=12_500_000)
 METRIC = "mrts_basis_evals_per_sec"
 UNIT = "basis_evals/s"
+K1_SOURCES = ("autofrk_b200/csrc/mrts_predict_kernel.cuh", "autofrk_b200/csrc/mrts_plan.cu")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -78,18 +80,40 @@ def summarize_clocks(samples):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores
+# CPU arm: the reference's own path on the host cores.
+#   kernel matrix: the reference's tpm_predict itself (src/autoFRK.cpp:109-153, compiled unmodified into
+#   oracle/_ref/libautofrk_ref.so) -- the plain-C restatement when that library was not built;
+#   projection:    OpenBLAS GEMM standing in for Eigen's (src/autoFRK.cpp:316-324), the port.
+# The reference runs the kernel loop on ONE thread; here every host core gets a row block (generous to the CPU).
 # ----------------------------------------------------------------------------------------------
-def cpu_predict_rows(Xu, UZ, BBBH, nconst, xnew, K, threads):
-    """predict.mrts on the CPU the way the reference does it: scalar C loop for the kernel matrix
-    (src/autoFRK.cpp:109-153, one row block per host thread), BLAS GEMM for the projection (:316-324)."""
+def _kernel_loop():
+    """(callable(xc_block, Xu_f, H_block), kind): fills H (rows x m, column-major, contiguous) for a block of rows."""
     import ctypes as C
 
-    from oracle.build_oracle import build_oracle
+    from oracle import build_oracle as ob
 
-    lib = C.CDLL(str(build_oracle()))
-    lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
-                                       C.c_int64]
+    if ob.build_ref() is not None:
+        from oracle import ref as R
+
+        L = R.lib()
+
+        def loop(xc, Xuf, H):
+            rc = L.ref_tpm_predict(C.c_void_p(xc.ctypes.data), C.c_int64(xc.shape[0]), C.c_void_p(Xuf.ctypes.data),
+                                   C.c_int64(Xuf.shape[0]), C.c_int(Xuf.shape[1]), C.c_int(Xuf.shape[1]), C.c_void_p(H.ctypes.data))
+            assert rc == 0
+        return loop, "ref+port"
+    lib = C.CDLL(str(ob.build_oracle()))
+    lib.oracle_tpm_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+
+    def loop(xc, Xuf, H):
+        n2 = xc.shape[0]
+        assert lib.oracle_tpm_predict(xc.ctypes.data, n2, n2, Xuf.ctypes.data, Xuf.shape[0], Xuf.shape[1], H.ctypes.data, n2) == 0
+    return loop, "port"
+
+
+def cpu_predict_rows(Xu, UZ, BBBH, nconst, xnew, K, threads, loop):
+    """predict.mrts on the CPU the way the reference does it: scalar loop for the kernel matrix (one contiguous row
+    block per host thread), BLAS GEMM for the projection, polynomial columns (R/autoFRK.R:1460-1466)."""
     n2_all, d = xnew.shape
     m = Xu.shape[0]
     kstar = K - d - 1
@@ -101,22 +125,24 @@ def cpu_predict_rows(Xu, UZ, BBBH, nconst, xnew, K, threads):
     chunk = 100_000                                   # the reference does not chunk (it would need n2*m*8 bytes)
     with ThreadPoolExecutor(threads) as ex:
         for c0 in range(0, n2_all, chunk):
-            xc = np.asfortranarray(xnew[c0:c0 + chunk])
+            xc = xnew[c0:c0 + chunk]
             n2 = xc.shape[0]
-            H = np.empty((n2, m), order="F")
-            blocks = np.linspace(0, n2, threads + 1).astype(np.int64)
+            cuts = np.linspace(0, n2, threads + 1).astype(np.int64)
+            blocks = [(int(cuts[i]), int(cuts[i + 1])) for i in range(threads) if cuts[i + 1] > cuts[i]]
 
-            def work(i):
-                r0, r1 = int(blocks[i]), int(blocks[i + 1])
-                if r1 > r0:
-                    lib.oracle_tpm_predict(xc.ctypes.data + 8 * r0, r1 - r0, n2, Xuf.ctypes.data, m, d,
-                                           H.ctypes.data + 8 * r0, n2)
+            def work(b):
+                xb = np.asfortranarray(xc[b[0]:b[1]])
+                H = np.empty((b[1] - b[0], m), order="F")
+                loop(xb, Xuf, H)
+                return H
 
-            list(ex.map(work, range(threads)))
-            X1 = H @ W - np.column_stack([np.ones(n2), xc]) @ Cpoly
-            out[c0:c0 + n2, 0] = 1.0
-            out[c0:c0 + n2, 1:d + 1] = (xc - shift) / nconst
-            out[c0:c0 + n2, d + 1:] = X1[:, :kstar]
+            Hs = list(ex.map(work, blocks))
+            for (r0, r1), H in zip(blocks, Hs):
+                xb = xc[r0:r1]
+                X1 = H @ W - np.column_stack([np.ones(r1 - r0), xb]) @ Cpoly
+                out[c0 + r0:c0 + r1, 0] = 1.0
+                out[c0 + r0:c0 + r1, 1:d + 1] = (xb - shift) / nconst
+                out[c0 + r0:c0 + r1, d + 1:] = X1[:, :kstar]
     return out
 
 
@@ -130,17 +156,32 @@ def oracle_fit(Xu, K):
 
 def run_cpu(sample_rows, steps, warmup, threads):
     w = WORKLOAD
+    loop, kind = _kernel_loop()
     Xu = make_knots(w["knots"], w["d"])
     fit = oracle_fit(Xu, w["K"])
     rng = np.random.default_rng(1234)
     x = rng.random((sample_rows, w["d"]))
     for _ in range(warmup):
-        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x[: max(1000, sample_rows // 10)], w["K"], threads)
+        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x[: max(1000, sample_rows // 10)], w["K"], threads, loop)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x, w["K"], threads)
+        cpu_predict_rows(Xu, fit["UZ"], fit["BBBH"], fit["nconst"], x, w["K"], threads, loop)
     dt = (time.perf_counter() - t0) / steps
-    return sample_rows * w["K"] / dt, dt
+    return sample_rows * w["K"] / dt, dt, kind
+
+
+def run_cpu_single_thread(sample_rows):
+    """the reference's kernel loop is single-threaded (src/autoFRK.cpp:124-151); one thread for the
+    GEMM too.  What one R process without a threaded BLAS would do."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:  # pragma: no cover
+        return None
+    with threadpool_limits(limits=1):
+        val, dt, kind = run_cpu(sample_rows, 1, 0, 1)
+    return {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{sample_rows} rows of the same workload ({dt:.1f} s): the reference's scalar kernel loop on one thread + "
+                      f"single-thread GEMM"}
 
 
 def main_reference(args):
@@ -149,17 +190,18 @@ def main_reference(args):
         return 0
     threads = os.cpu_count() or 1
     rows = 400_000
-    val, dt = run_cpu(rows, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
+    val, dt, kind = run_cpu(rows, max(1, args.steps), max(1, min(args.warmup, 1)), threads)
     w = WORKLOAD
+    how = ("the reference's own tpm_predict (oracle/_ref: src/autoFRK.cpp compiled unmodified), one row block per thread"
+           if kind == "ref+port" else "scalar C restatement of tpm_predict, one row block per thread")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"predict.mrts: {w['rows_per_gpu']} 2-D locations/GPU x {w['knots']} knots, K={w['K']}",
                    "sample": f"{rows} rows per step (the path is linear in rows)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows} rows x {w['knots']} knots x K={w['K']} per step; scalar C kernel loop "
-                                   f"(one row block per thread) + OpenBLAS GEMM"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{rows} rows x {w['knots']} knots x K={w['K']} per step; {how} + OpenBLAS GEMM"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -171,8 +213,10 @@ def main_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 def measure_dgemm_peak(torch, n=8192, reps=5):
-    a = torch.zeros((n, n), dtype=torch.float64, device="cuda")
-    b = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    """cuBLAS DGEMM on random operands (not zeros: zeros toggle fewer bits and can run at a higher clock)."""
+    g = torch.Generator(device="cuda").manual_seed(99)
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
     c = torch.empty((n, n), dtype=torch.float64, device="cuda")
     torch.matmul(a, b, out=c)
     torch.cuda.synchronize()
@@ -187,6 +231,38 @@ def measure_dgemm_peak(torch, n=8192, reps=5):
     del a, b, c
     torch.cuda.empty_cache()
     return 2.0 * n ** 3 / best / 1e9
+
+
+def measure_dmma_peak():
+    import ctypes as C
+
+    from autofrk_b200._lib import check, lib
+
+    t = C.c_double(0.0)
+    check(lib.frk_measure_dmma_peak(20000, C.byref(t)))
+    return float(t.value)
+
+
+def measured_peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        return {}
+
+
+def timed(torch, f, reps=2):
+    """best CUDA-event time of f() on the current stream after one warm-up call, ms"""
+    f()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        f()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
 
 
 def main_gpu(args):
@@ -218,6 +294,7 @@ def main_gpu(args):
     plan = basis.plan()
 
     dgemm_peak = measure_dgemm_peak(torch) if rank == 0 else None
+    dmma_peak = measure_dmma_peak() if rank == 0 else None
 
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=gen).T        # 200 MB > L2
@@ -253,30 +330,43 @@ def main_gpu(args):
     ms_step = float(ms_total.item()) / args.steps
     value = world * n2 * K / (ms_step * 1e-3)
 
-    # end to end through the host-buffer API (pinned host memory, H2D + D2H inside the timed region)
+    def max_over_ranks(seconds):
+        t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def wall(f, reps):
+        f()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / reps)
+
+    # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region) --------------------
     n2e = min(n2, args.e2e_rows)
+    e2e_steps = max(1, min(args.steps, 3))
     xh = torch.empty((d, n2e), dtype=torch.float64).pin_memory()
     xh.copy_(x.T[:, :n2e])
     oh = torch.empty((K, n2e), dtype=torch.float64).pin_memory()
     xh_np, oh_np = xh.numpy().T, oh.numpy().T                                          # column-major views
-    plan.predict(xh_np, mode=FRK_OUT_BASIS, out=oh_np)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        plan.predict(xh_np, mode=FRK_OUT_BASIS, out=oh_np)
-    torch.cuda.synchronize()
-    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = world * n2e * K / float(dt.item())
-    # the two paths run the same kernel on the same rows
-    same = bool(torch.equal(torch.from_numpy(oh_np[:1000].copy()), out[:1000].cpu()))
+    e2e_val = world * n2e * K / wall(lambda: plan.predict(xh_np, mode=FRK_OUT_BASIS, out=oh_np), e2e_steps)
+    same = bool(torch.equal(torch.from_numpy(oh_np[:1000].copy()), out[:1000].cpu()))   # same kernel, same rows
+    # what `.Call` hands over: pageable R vectors (the library stages such results through pinned memory)
+    x_page = np.asfortranarray(xh_np)
+    out_page = np.zeros((n2e, K), order="F")
+    e2e_page = world * n2e * K / wall(lambda: plan.predict(x_page, mode=FRK_OUT_BASIS, out=out_page), e2e_steps)
+    same_page = bool(np.array_equal(out_page[:1000], oh_np[:1000]))
+    del oh, oh_np, out_page
+    # the calls autoFRK() / predict.FRK() make at scale return K x K + K x T + 1 numbers or n2 x (T + 1), not n2 x K
+    fused = fused_e2e(plan, x_page, K, wall, world)
 
-    fit_block = fit_benchmarks(torch, dist, world, rank, basis, x, args) if not args.no_fit else None
+    del out
+    torch.cuda.empty_cache()
+    fit_block = fit_benchmarks(torch, dist, world, rank, basis, x, args, dgemm_peak) if not args.no_fit else None
     if fit_block is not None and world == 1:   # BASELINE configs[1] and configs[2] at full size, beside the headline
-        del out
-        torch.cuda.empty_cache()
         fit_block["other_configs"] = other_configs(torch)
 
     if rank == 0:
@@ -285,12 +375,15 @@ def main_gpu(args):
         threads = os.cpu_count() or 1
         cpu_rows = 2_000_000
         if world == 1:   # the CPU baseline is timed on rank 0 at N = 1 only
-            cpu_val, cpu_dt = run_cpu(cpu_rows, 1, 1, threads)
-            cpu_block = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{cpu_rows} rows of the same workload ({cpu_dt:.1f} s): scalar C kernel loop "
-                                   f"(src/autoFRK.cpp:109-153, one row block per thread) + OpenBLAS GEMM"}
+            cpu_val, cpu_dt, kind = run_cpu(cpu_rows, 1, 1, threads)
+            cpu_block = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{cpu_rows} rows of the same workload ({cpu_dt:.1f} s): "
+                                   + ("the reference's own tpm_predict (oracle/_ref = src/autoFRK.cpp:109-153 compiled "
+                                      "unmodified)" if kind == "ref+port" else "scalar C restatement of src/autoFRK.cpp:109-153")
+                                   + ", one row block per thread, + OpenBLAS GEMM for the projection",
+                         "single_thread": run_cpu_single_thread(100_000)}
         else:
-            cpu_block = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": "timed at N=1 only"}
+            cpu_block = {"value": None, "unit": UNIT, "cores": threads, "kind": "ref+port", "sample": "timed at N=1 only"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -306,7 +399,10 @@ def main_gpu(args):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": dgemm_peak, "unit": "TFLOP/s",
                 "frac": achieved / dgemm_peak,
-                "peak_source": "FP64: cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json holds no FP64 peak)",
+                "peak_source": "FP64: cuBLAS DGEMM 8192^3 on random operands, measured in this run (MEASURED_PEAKS.json "
+                               "holds no FP64 peak; cuBLAS runs an sm_80 CUTLASS DGEMM here, so this is a library figure)",
+                "peak_dmma_issue": dmma_peak, "frac_of_dmma_issue": achieved / dmma_peak,
+                "peak_dmma_issue_source": "frk_measure_dmma_peak: DMMA.8x8x4 issue rate of this device, measured in this run",
                 "flops_per_launch": flops, **k1_traffic(n2, m, K),
                 "kernel": "mrts_predict_kernel (DMMA.8x8x4)",
             },
@@ -314,7 +410,11 @@ def main_gpu(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n2e * d * 8),
                     "d2h_bytes_per_step": int(n2e * K * 8),
                     "sample": f"{n2e} rows/GPU per step through frk_plan_predict (host buffers, pinned)",
-                    "matches_device_path": same, "cpus_bound_to_gpu_socket": numa_cpus},
+                    "matches_device_path": same, "cpus_bound_to_gpu_socket": numa_cpus,
+                    "pageable": {"value": e2e_page, "unit": UNIT, "matches_pinned": same_page,
+                                 "note": "pageable host buffers, as R hands them to .Call: staged through the plan's pinned "
+                                         "ring + host scatter threads"},
+                    "fused": fused},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
         }
@@ -324,6 +424,30 @@ def main_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def fused_e2e(plan, x_page, K, wall, world):
+    """frk_plan_predict_gram (host x, Z -> G, C, zz) and frk_plan_predict_frk (host x -> yhat, se): the n2 x K basis never
+    exists, so the host side moves n2 x (d + T) in and K x K (or n2 x (T + 1)) out."""
+    from autofrk_b200._lib import check, lib, ptr
+
+    n2e, d = x_page.shape
+    rng = np.random.default_rng(3)
+    out = {}
+    Z = np.asfortranarray(rng.standard_normal((n2e, 1)))
+    Gm, Cm, zz = np.empty((K, K), order="F"), np.empty((K, 1), order="F"), np.zeros(1)
+    t = wall(lambda: check(lib.frk_plan_predict_gram(plan._h, ptr(x_page), n2e, ptr(Z), 1, None, ptr(Gm), ptr(Cm), ptr(zz))), 2)
+    out["predict_gram_T1"] = {"value": world * n2e * K / t, "unit": UNIT, "wall_ms": t * 1e3,
+                              "h2d_bytes_per_step": int(n2e * (d + 1) * 8), "d2h_bytes_per_step": int((K * K + K + 1) * 8)}
+    wv = np.asfortranarray(rng.standard_normal((K, 1)))
+    R = rng.standard_normal((K, 3))
+    V = np.asfortranarray(R @ R.T)
+    yh, se = np.empty((n2e, 1), order="F"), np.empty(n2e)
+    t = wall(lambda: check(lib.frk_plan_predict_frk(plan._h, ptr(x_page), n2e, ptr(wv), 1, ptr(V), ptr(yh), ptr(se))), 2)
+    out["predict_frk_T1_rank3"] = {"value": world * n2e * K / t, "unit": UNIT, "wall_ms": t * 1e3,
+                                   "h2d_bytes_per_step": int(n2e * d * 8), "d2h_bytes_per_step": int(n2e * 2 * 8)}
+    out["sample"] = f"{n2e} rows/GPU per call, pageable host buffers; value = n2 * K / wall (the basis columns the call stands for)"
+    return out
 
 
 def other_configs(torch):
@@ -347,16 +471,7 @@ def other_configs(torch):
         gen = torch.Generator(device="cuda").manual_seed(77)
         x = torch.rand((d, n2), dtype=torch.float64, device="cuda", generator=gen).T
         out = torch.empty((K, n2), dtype=torch.float64, device="cuda").T
-        plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
-        torch.cuda.synchronize()
-        best = 1e30
-        for _ in range(2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            plan.predict_dev(x, out, mode=FRK_OUT_BASIS)
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+        best = timed(torch, lambda: plan.predict_dev(x, out, mode=FRK_OUT_BASIS))
         kstar = K - d - 1
         res[name] = {"d": d, "knots": m, "K": K, "locations": n2, "mrts_fit_wall_ms": t_fit * 1e3, "predict_ms": best,
                      "basis_evals_per_s": n2 * K / (best * 1e-3), "tflops_credited": 2.0 * n2 * m * kstar / best / 1e9,
@@ -366,71 +481,147 @@ def other_configs(torch):
     return res
 
 
+def sources_sha256(paths):
+    h = hashlib.sha256()
+    for p in paths:
+        h.update((ROOT / p).read_bytes())
+    return h.hexdigest()
+
+
 def k1_traffic(n2, m, K):
-    """DRAM bytes (read + write) of one K1 launch from the committed `ncu --set full` capture of this exact workload
-    (profiles/k1_traffic_r01.json); None for any other shape."""
+    """DRAM bytes (read + write) of one K1 launch from the committed `ncu --set full` capture of this exact workload,
+    valid only while the kernel sources still hash to what was captured; None otherwise."""
+    detail = {"k1_sources_sha256_now": sources_sha256(K1_SOURCES)}
     try:
-        t = json.loads((ROOT / "profiles" / "k1_traffic_r01.json").read_text())
-        if (n2, m, K) == (12_500_000, 1000, 500):
-            return {"traffic": t["traffic_bytes"],      # bytes per launch (a plain number, like `achieved`)
-                    "traffic_detail": {"algorithmic_bytes": t["algorithmic_bytes"], "unit": "B", "source":
-                                       "profiles/k1_traffic_r01.json (ncu --set full of this launch, "
-                                       "dram__bytes_read.sum + dram__bytes_write.sum; kernel arithmetic unchanged since)"}}
-    except Exception:
-        pass
-    return {"traffic": None}
+        t = json.loads((ROOT / "profiles" / "k1_traffic_r02.json").read_text())
+        detail.update({"algorithmic_bytes": t["algorithmic_bytes"], "unit": "B", "captured_at_commit": t.get("commit"),
+                       "k1_sources_sha256_at_capture": t.get("k1_sources_sha256"),
+                       "source": "profiles/k1_traffic_r02.json (ncu --set full of this launch, dram__bytes_read.sum + "
+                                 "dram__bytes_write.sum); not re-measured by this run"})
+        if (n2, m, K) == (12_500_000, 1000, 500) and t.get("k1_sources_sha256") == detail["k1_sources_sha256_now"]:
+            return {"traffic": t["traffic_bytes"], "traffic_detail": detail}
+        detail["why_null"] = "kernel sources changed since the capture, or another shape"
+    except Exception as e:
+        detail["why_null"] = f"no capture: {e!r}"[:200]
+    return {"traffic": None, "traffic_detail": detail}
 
 
-def fit_benchmarks(torch, dist, world, rank, basis, x, args):
+def gram_points(torch, basis, x, dgemm_peak):
+    """K4 against its rooflines: BASELINE configs[3] (5 M x 500, T = 100: tensor-bound) with F produced by K1,
+    and the shapes default autoFRK() selects, down to the HBM-bound K = 32 point."""
+    import ctypes as C
+
+    from autofrk_b200._lib import FRK_OUT_BASIS, check, lib
+
+    hbm = measured_peaks().get("hbm_gbs")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = {"hbm_peak_gbs": hbm, "hbm_peak_source": "MEASURED_PEAKS.json (copy bandwidth)" if hbm else "unavailable"}
+    n = min(5_000_000, x.shape[0])
+
+    def run(F, Z, K, T):
+        packed = torch.empty(lib.frk_gram_packed_len(K, T), dtype=torch.float64, device="cuda")
+        ms = timed(torch, lambda: check(lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), n, K, F.stride(1), C.c_void_p(Z.data_ptr()),
+                                                               T, Z.stride(1) if T > 1 else n, None, C.c_void_p(packed.data_ptr()), st)), 3)
+        flops = n * K * (K + 1.0) + 2.0 * n * K * T + 2.0 * n * T
+        gbs = 8.0 * n * (K + T) / ms / 1e6
+        r = {"n": n, "K": K, "T": T, "ms": ms, "tflops_credited": flops / ms / 1e9, "gbs": gbs}
+        if dgemm_peak:
+            r["frac_of_dgemm"] = r["tflops_credited"] / dgemm_peak
+        if hbm:
+            r["frac_of_hbm"] = gbs / hbm
+        return r
+
+    K = basis.X.shape[1]
+    F = torch.empty((K, n), dtype=torch.float64, device="cuda").T
+    basis.plan().predict_dev(x[:n], F, mode=FRK_OUT_BASIS)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Z = torch.randn((100, n), dtype=torch.float64, device="cuda", generator=g).T
+    res["configs[3]_K500_T100"] = run(F, Z, K, 100)
+    res["K500_T1"] = run(F, Z, K, 1)
+    for Ks, T in ((128, 4), (100, 1), (64, 4), (32, 4)):
+        res[f"K{Ks}_T{T}"] = run(F[:, :Ks], Z, Ks, T)
+    res["note"] = ("device-resident F = predict.mrts output of K1 (leading K columns), Z = N(0,1); CUDA events, best of 3; "
+                   "tflops_credited = n K (K+1) + 2 n K T + 2 n T flops; gbs = 8 n (K + T) bytes")
+    del F, Z
+    torch.cuda.empty_cache()
+    return res
+
+
+def fit_benchmarks(torch, dist, world, rank, basis, x, args, dgemm_peak):
     """Secondary metric of BASELINE.json: fit wall time.
-    (i) configs[3]/[4]-shaped cMLE fit: rows_fit locations/GPU x K=500, T=100, basis evaluated on the fly (never
-        materialised), one all-reduce of [G|C|zz], replicated K x K stage;
-    (ii) configs[0]: autoFRK(Data=z, loc=s) on 2,000 random 2-D locations, default basis -- GPU vs the oracle."""
+    (i) configs[3]/[4]-shaped cMLE fit: --fit-rows locations/GPU (default: the workload's 12.5 M) x K=500, T=1 and T=100,
+        basis evaluated on the fly (never materialised), ONE collective of [G|C|zz], replicated K x K stage;
+    (ii) K4 against its rooflines; (iii) configs[0]: autoFRK(Data=z, loc=s) on 2,000 random 2-D locations."""
     from autofrk_b200 import dist as D
+    from autofrk_b200._lib import lib as _l
+    from autofrk_b200.frk import cmle_from_stats
 
     out = {}
     K = basis.X.shape[1]
-    T = 100
     rows = min(x.shape[0], args.fit_rows)
     plan = basis.plan()
-    gen = torch.Generator(device="cuda").manual_seed(11 + rank)
-    Z = torch.randn((T, rows), dtype=torch.float64, device="cuda", generator=gen).T
     xs = x[:rows]
-    D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True)       # warm-up (workspaces, cuSOLVER handles)
-    peer = None
-    if world > 1:
-        try:   # the collective as our own NVLink peer-memory kernel (falls back to NCCL if symmetric memory is unavailable)
-            from autofrk_b200._lib import lib as _l
-            peer = D.PeerAllReduce(_l.frk_gram_packed_len(K, T), xs.device)
-            D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True, peer=peer)
-        except Exception:
-            peer = None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    t0 = time.perf_counter()
-    e0.record()
-    packed = D.predict_gram_shard(plan, xs, Z, out=None if peer is None else peer.buf)
-    e1.record()
-    packed = peer() if peer is not None else D.allreduce_stats(packed)
-    e2.record()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    from autofrk_b200.frk import cmle_from_stats
-    res = cmle_from_stats(packed[:K * K], packed[K * K:K * K + K * T], float(packed[-1].item()), rows * world, T,
-                          s=0.0, wSave=True, onlylogLike=False, K=K, on_device=True)
-    t2 = time.perf_counter()
-    gram_flops = rows * (K * (K + 1.0) + 2.0 * K * T + 2.0 * T)
-    out["cmle_sharded"] = {
-        "rows_per_gpu": rows, "K": K, "T": T, "predict_gram_ms": e0.elapsed_time(e1), "allreduce_ms": e1.elapsed_time(e2),
-        "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
-        "collective": "none (1 GPU)" if world == 1 else ("frk_peer_sum_dev over NVLink peer memory" if peer is not None
-                                                        else "NCCL all_reduce"),
-        "note": "predict_gram = K1 (basis on the fly, 2 GB chunks) + K4 (Gram/cross-products); credited Gram flops "
-                f"{gram_flops:.3e} per GPU"}
-    if rank == 0:   # predict.FRK (yhat + se) at new locations with the fit above, first replicate: host buffers in and out
-        from autofrk_b200._lib import check as _check, lib as _l, ptr as _ptr
+    out["cmle_sharded"] = []
+    res = None
+    for T in (1, 100):
+        gen = torch.Generator(device="cuda").manual_seed(11 + rank)
+        Z = torch.randn((T, rows), dtype=torch.float64, device="cuda", generator=gen).T
+        D.fit_sharded(plan, xs, Z, n_total=rows * world, wSave=True)       # warm-up (workspaces, cuSOLVER handles); NCCL
+        peer, check, fallback = None, None, None
+        if world > 1:
+            # the collective as our own NVLink peer-memory kernel, checked against NCCL's all-reduce of the same buffers
+            try:
+                peer = D.PeerAllReduce(_l.frk_gram_packed_len(K, T), xs.device)
+                D.predict_gram_shard(plan, xs, Z, out=peer.buf)
+                nccl_sum = peer.buf.clone()
+                dist.all_reduce(nccl_sum, op=dist.ReduceOp.SUM)
+                peer_sum = peer().clone()
+                rel = float((peer_sum - nccl_sum).abs().max() / nccl_sum.abs().max())
+                ref0 = peer_sum.clone()
+                dist.broadcast(ref0, src=0)
+                same = torch.tensor([int(torch.equal(ref0, peer_sum))], device="cuda")
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                check = {"peer_vs_nccl_max_rel_diff": rel, "bitwise_identical_on_all_ranks": bool(same.item() == 1)}
+            except Exception as e:   # reported, never swallowed: the line says which collective ran and why
+                peer, fallback = None, repr(e)[:300]
+            flag = torch.tensor([0 if peer is None else 1], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)                    # all ranks take the same path
+            if flag.item() == 0:
+                peer = None
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t0 = time.perf_counter()
+        e0.record()
+        packed = D.predict_gram_shard(plan, xs, Z, out=None if peer is None else peer.buf)
+        e1.record()
+        packed = peer() if peer is not None else D.allreduce_stats(packed)
+        e2.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        res = cmle_from_stats(packed[:K * K], packed[K * K:K * K + K * T], float(packed[-1].item()), rows * world, T,
+                              s=0.0, wSave=True, onlylogLike=False, K=K, on_device=True)
+        t2 = time.perf_counter()
+        # the same collective through NCCL, timed on the same buffer (first-class path, also the fallback)
+        nccl_ms = None
+        if world > 1:
+            buf = packed.clone()
+            nccl_ms = timed(torch, lambda: dist.all_reduce(buf, op=dist.ReduceOp.SUM), 3)
+        gram_flops = rows * (K * (K + 1.0) + 2.0 * K * T + 2.0 * T)
+        out["cmle_sharded"].append({
+            "rows_per_gpu": rows, "K": K, "T": T, "predict_gram_ms": e0.elapsed_time(e1), "collective_ms": e1.elapsed_time(e2),
+            "nccl_allreduce_ms": nccl_ms, "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
+            "collective": "none (1 GPU)" if world == 1 else ("frk_peer_sum_dev over NVLink peer memory" if peer is not None
+                                                            else "NCCL all_reduce"),
+            "check": check, "collective_fallback_reason": fallback,
+            "note": "predict_gram = K1 (basis on the fly, 2 GB chunks) + K4 (Gram/cross-products); credited Gram flops "
+                    f"{gram_flops:.3e} per GPU"})
+        del Z, peer
+        torch.cuda.empty_cache()
+    if rank == 0:
+        out["gram"] = gram_points(torch, basis, x, dgemm_peak)
+    if rank == 0:   # predict.FRK (yhat + se) at new locations with the T = 100 fit above, first replicate: host buffers
+        from autofrk_b200._lib import check as _check, ptr as _ptr
         n_new = min(rows, 4_000_000)
         xn = np.asfortranarray(xs[:n_new].cpu().numpy())
         w1 = np.asfortranarray(res["w"][:, :1])
@@ -473,16 +664,14 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args):
 
 
 def fit_for_bench(Xu, K):
-    """mrts fit of the knots.  Uses the device fit when the library provides it; the eigenvector
-    block is replicated, so computing it once per process is part of setup, not of the timed path."""
+    """mrts fit of the knots on the device.  The eigenvector block is replicated, so computing it once per process is
+    part of setup, not of the timed path."""
     from autofrk_b200 import mrts as G
 
     m, d = Xu.shape
-    if hasattr(G, "mrtsrcpp"):
-        r = G.mrtsrcpp(Xu, G.xobs_diag_of(Xu, m), K - d - 1)
-        r["how"] = "frk_mrtsrcpp on device"
-        return r
-    raise SystemExit("device fit unavailable")
+    r = G.mrtsrcpp(Xu, G.xobs_diag_of(Xu, m), K - d - 1)
+    r["how"] = "frk_mrtsrcpp on device"
+    return r
 
 
 def main():
@@ -492,8 +681,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's 12.5M)")
-    ap.add_argument("--e2e-rows", type=int, default=1_000_000)
-    ap.add_argument("--fit-rows", type=int, default=5_000_000, help="rows per GPU of the cMLE fit timing")
+    ap.add_argument("--e2e-rows", type=int, default=4_000_000)
+    ap.add_argument("--fit-rows", type=int, default=WORKLOAD["rows_per_gpu"], help="rows per GPU of the cMLE fit timing")
     ap.add_argument("--no-fit", action="store_true", help="skip the secondary fit timings")
     ap.add_argument("--fit-oracle", type=int, default=1, help="also time the CPU oracle's autoFRK at configs[0]")
     args = ap.parse_args()

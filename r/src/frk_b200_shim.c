@@ -1,11 +1,12 @@
-/* .Call shim binding autoFRK's four registered native routines (src/RcppExports.cpp:71-77) to
- * libfrk_b200.so.  Written against R's C API only (Rinternals.h); NOT compiled in the build
- * container (R is not installed there) -- the identical C ABI is exercised through ctypes.
+/* .Call shim binding autoFRK's four registered native routines (src/RcppExports.cpp:71-77), plus the new
+ * routines the R overlay (r/R/overrides.R) calls, to libfrk_b200.so.  Written against R's C API only
+ * (Rinternals.h).  R is not installed in the build container: there the file is compiled against declarations of
+ * that API (tests/r_stub) and EXECUTED against a small mock of it (tests/r_stub/mock_r.c, tests/test_r_shim_gpu.py),
+ * which checks argument marshalling, the returned list layouts and the error path; linking against a real R is the
+ * one step left to a maintainer (r/README.md).
  *
- * Build inside the package:   PKG_LIBS = -L$(FRK_B200_HOME)/autofrk_b200 -lfrk_b200
- *                             PKG_CPPFLAGS = -I$(FRK_B200_HOME)/include
- * and drop src/autoFRK.cpp + src/RcppExports.cpp (this file replaces both; LinkingTo: Rcpp,
- * RcppEigen, RSpectra are no longer needed).
+ * Build inside the package: r/src/Makevars; drop src/autoFRK.cpp + src/RcppExports.cpp (this file replaces both;
+ * LinkingTo: Rcpp, RcppEigen, RSpectra are no longer needed).
  *
  * Conventions honoured: arguments are REALSXP matrices read in place (column-major,
  * dims from the dim attribute; integer input is an error exactly as with Eigen::Map<MatrixXd>),
@@ -159,6 +160,79 @@ SEXP _autoFRK_cMLEimat_sweep(SEXP G, SEXP C, SEXP zz, SEXP TT_, SEXP n_, SEXP s_
     return nll;   /* NaN entries: the caller uses _autoFRK_cMLEimat_stats on the leading blocks for that K */
 }
 
+/* ---- routines behind r/R/overrides.R ------------------------------------------------------------------------ */
+static frk_plan *plan_of(SEXP Xu, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP K_) {
+    need_real_matrix(Xu, "Xu"); need_real_matrix(BBBH, "BBBH"); need_real_matrix(UZ, "UZ"); need_real_matrix(nconst, "nconst");
+    frk_plan *plan = NULL;
+    /* predict.mrts passes k = NCOL(object) (R/autoFRK.R:1458): the trailing d+1 zero columns are detected and skipped */
+    check(frk_plan_create(&plan, REAL(Xu), nrow_of(Xu), ncol_of(Xu), REAL(BBBH), REAL(UZ), nrow_of(UZ), ncol_of(UZ),
+                          REAL(nconst), Rf_asInteger(K_), 0));
+    return plan;
+}
+/* a failing call must release the plan before Rf_error() longjmps away */
+static void check_plan(frk_plan *plan, int32_t status) {
+    if (status != FRK_OK) {
+        frk_plan_destroy(plan);
+        Rf_error("%s", frk_last_error());
+    }
+}
+
+/* predict.mrts body (R/autoFRK.R:1453-1466): cbind(1, (x0 - shift) / nconst, X1[, 1:kstar]) in one kernel pass */
+SEXP _autoFRK_predict_mrts_basis(SEXP Xu, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP K_, SEXP xnew) {
+    need_real_matrix(xnew, "xnew");
+    if (ncol_of(xnew) != ncol_of(Xu)) Rf_error("xnew must have %d columns", ncol_of(Xu));   /* src/autoFRK.cpp:299 */
+    int64_t n2 = nrow_of(xnew); int K = Rf_asInteger(K_);
+    frk_plan *plan = plan_of(Xu, BBBH, UZ, nconst, K_);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)n2, K));
+    check_plan(plan, frk_plan_predict(plan, REAL(xnew), n2, REAL(out), FRK_OUT_BASIS));
+    frk_plan_destroy(plan);
+    UNPROTECT(1);
+    return out;
+}
+
+/* the sufficient statistics of cMLEimat on the mrts basis at `xnew` without forming it: list(G, C, zz)
+ * (R/helper.R:20, R/autoFRK.R:431-435 fused behind R/autoFRK.R:1453-1466) */
+SEXP _autoFRK_predict_gram(SEXP Xu, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP K_, SEXP xnew, SEXP Data) {
+    need_real_matrix(xnew, "xnew"); need_real_matrix(Data, "Data");
+    if (ncol_of(xnew) != ncol_of(Xu)) Rf_error("xnew must have %d columns", ncol_of(Xu));
+    if (nrow_of(Data) != nrow_of(xnew)) Rf_error("Data must have one row per location");
+    int64_t n2 = nrow_of(xnew); int K = Rf_asInteger(K_), T = ncol_of(Data);
+    frk_plan *plan = plan_of(Xu, BBBH, UZ, nconst, K_);
+    const char *names[] = {"G", "C", "zz"};
+    SEXP out = PROTECT(named_list(3, names));
+    SEXP G = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    SEXP C = PROTECT(Rf_allocMatrix(REALSXP, K, T));
+    SEXP zz = PROTECT(Rf_allocVector(REALSXP, 1));
+    check_plan(plan, frk_plan_predict_gram(plan, REAL(xnew), n2, REAL(Data), T, NULL, REAL(G), REAL(C), REAL(zz)));
+    frk_plan_destroy(plan);
+    SET_VECTOR_ELT(out, 0, G); SET_VECTOR_ELT(out, 1, C); SET_VECTOR_ELT(out, 2, zz);
+    UNPROTECT(4);
+    return out;
+}
+
+/* predict.FRK at new locations of an mrts model (R/autoFRK.R:1184,1216,1220): list(yhat n2 x T, se n2 or NULL);
+ * V = R_NilValue skips the standard errors */
+SEXP _autoFRK_predict_frk(SEXP Xu, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP K_, SEXP xnew, SEXP w, SEXP V) {
+    need_real_matrix(xnew, "xnew"); need_real_matrix(w, "w");
+    int K = Rf_asInteger(K_), T = ncol_of(w);
+    int64_t n2 = nrow_of(xnew);
+    const int want_se = TYPEOF(V) == REALSXP;
+    if (ncol_of(xnew) != ncol_of(Xu)) Rf_error("xnew must have %d columns", ncol_of(Xu));
+    if (nrow_of(w) != K || (want_se && (Rf_nrows(V) != K || Rf_ncols(V) != K)))
+        Rf_error("Dimensions of basis and object$w are not compatible!");
+    frk_plan *plan = plan_of(Xu, BBBH, UZ, nconst, K_);
+    const char *names[] = {"yhat", "se"};
+    SEXP out = PROTECT(named_list(2, names));
+    SEXP yhat = PROTECT(Rf_allocMatrix(REALSXP, (int)n2, T));
+    SEXP se = PROTECT(want_se ? Rf_allocVector(REALSXP, n2) : R_NilValue);
+    check_plan(plan, frk_plan_predict_frk(plan, REAL(xnew), n2, REAL(w), T, want_se ? REAL(V) : NULL, REAL(yhat),
+                                          want_se ? REAL(se) : NULL));
+    frk_plan_destroy(plan);
+    SET_VECTOR_ELT(out, 0, yhat); SET_VECTOR_ELT(out, 1, se);
+    UNPROTECT(3);
+    return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_getASCeigens", (DL_FUNC)&_autoFRK_getASCeigens, 1},
     {"_autoFRK_mrtsrcpp", (DL_FUNC)&_autoFRK_mrtsrcpp, 3},
@@ -168,6 +242,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_getHalf_stats", (DL_FUNC)&_autoFRK_getHalf_stats, 1},
     {"_autoFRK_cMLEimat_stats", (DL_FUNC)&_autoFRK_cMLEimat_stats, 6},
     {"_autoFRK_cMLEimat_sweep", (DL_FUNC)&_autoFRK_cMLEimat_sweep, 7},
+    {"_autoFRK_predict_mrts_basis", (DL_FUNC)&_autoFRK_predict_mrts_basis, 6},
+    {"_autoFRK_predict_gram", (DL_FUNC)&_autoFRK_predict_gram, 7},
+    {"_autoFRK_predict_frk", (DL_FUNC)&_autoFRK_predict_frk, 8},
     {NULL, NULL, 0}};
 
 void R_init_autoFRK(DllInfo *dll) {

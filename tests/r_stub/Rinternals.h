@@ -11,6 +11,9 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define STRSXP 16
 #define VECSXP 19
 extern SEXP R_NamesSymbol;
+extern SEXP R_NilValue;
+#define NILSXP 0
+#define LGLSXP 10
 int TYPEOF(SEXP);
 Rboolean Rf_isMatrix(SEXP);
 R_xlen_t XLENGTH(SEXP);

@@ -49,16 +49,12 @@ def test_product_never_imports_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), p
 
 
-def test_header_is_plain_c_and_shim_type_checks():
-    """include/frk_b200.h must parse as C (no C++ in the ABI); the R `.Call` shim type-checks against minimal
-    declarations of the R API (tests/r_stub) -- R itself is not installed in the build container."""
+def test_header_is_plain_c():
+    """include/frk_b200.h must parse as C (no C++ in the ABI).  (The R `.Call` shim is checked in test_r_shim.py.)"""
     import subprocess
 
     r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-x", "c", str(ROOT / "include" / "frk_b200.h")],
                        capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", f"-I{ROOT / 'tests' / 'r_stub'}", f"-I{ROOT / 'include'}",
-                        str(ROOT / "r" / "frk_b200_shim.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "error" not in r.stderr
 

@@ -550,3 +550,35 @@ def test_cMLEimat_scale_equivariance():
     assert abs(rs["negloglik"] - base["negloglik"]) <= 1e-10 * abs(base["negloglik"])
     assert relmax(rs["M"], base["M"] / np.outer(c, c)) < 1e-9
     assert relmax(rs["w"], base["w"] / c[:, None]) < 1e-9
+
+
+def test_predict_FRK_argument_contract():
+    """Corners of predict.FRK the reference treats specially (R/autoFRK.R:1214-1245): a model fitted with missing data has
+    per-replicate standard errors (not implemented here: loud, never a wrong se); obsloc without obsData leaves yhat
+    undefined in R; w / V that do not match the basis are rejected before the device reads them."""
+    from autofrk_b200 import frk as G, mrts as GM
+
+    rng = np.random.default_rng(8)
+    n, K = 600, 12
+    loc = rng.random((n, 2))
+    Fg = GM.mrts(loc[:100], K, loc)
+    z = (Fg.X[:, 3:5] @ np.array([2.0, -1.0]) + 0.3 * rng.standard_normal(n)).reshape(-1, 1)
+    obj = G.autoFRK(z, loc, G=Fg)
+    newloc = rng.random((50, 2))
+    ok = G.predict_FRK(obj, newloc=newloc, se_report=True)
+    assert ok["pred.value"].shape == (50, 1) and ok["se"].shape == (50, 1)
+    with pytest.raises(ValueError, match="obsloc was given without obsData"):
+        G.predict_FRK(obj, obsloc=newloc)
+    bad = dict(obj)
+    bad["w"] = obj["w"][:-1]
+    with pytest.raises(ValueError, match="Dimensions of basis and object\\$w"):
+        G.predict_FRK(bad, newloc=newloc)
+    bad = dict(obj)
+    bad["V"] = obj["V"][:-1, :-1]
+    with pytest.raises(ValueError, match="object\\$V"):
+        G.predict_FRK(bad, newloc=newloc, se_report=True)
+    miss = dict(obj)
+    miss["missing"] = {"miss": np.zeros((n, 1))}
+    assert G.predict_FRK(miss, newloc=newloc)["pred.value"].shape == (50, 1)       # yhat is the same formula (:1216)
+    with pytest.raises(NotImplementedError, match="per-replicate"):
+        G.predict_FRK(miss, newloc=newloc, se_report=True)
