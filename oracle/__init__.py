@@ -4,14 +4,16 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
 legs of ``bench.py`` may import anything from this package.  The product package
 (``autofrk_b200``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference (egpivo/autoFRK v1.4.4) ships no tests, golden vectors or
-fixtures for this path, R is not installed in the build container and
-``src/autoFRK.cpp`` cannot be compiled here (Rcpp / RcppEigen / RSpectra headers are absent,
-versions unpinned in DESCRIPTION:24).  The oracle is therefore a line-by-line restatement
-(numpy for the dense algebra, plain C for the scalar kernel loops), each function citing the
-reference file:line it follows, cross-checked by
+PARITY: pinned to the reference's own source for everything ``src/autoFRK.cpp`` holds, unpinned for the R code.
+The reference (egpivo/autoFRK v1.4.4) ships no tests, golden vectors or fixtures for this path
+and R is not installed in the build container.  Its C++ translation unit IS compiled here, unmodified, behind stand-in
+Rcpp / Eigen / Spectra headers (``oracle/stub/``, ``oracle/ref_wrap.cpp`` -> ``oracle/_ref/libautofrk_ref.so``, bound by
+``oracle/ref.py``); ``tests/test_oracle_ref.py`` checks this restatement against it and against the vectors it
+generated (``tests/golden/ref_vectors.npz``): the scalar kernel loops bit for bit, the fit / predict wrappers to
+rounding level, every argument-check message verbatim.  The R-level functions (``frk_oracle.py``, the front-ends in
+``mrts_oracle.py``) have no executable reference here; they are a line-by-line restatement (numpy for the dense algebra),
+each function citing the reference file:line it follows, cross-checked by
 
-  * the C restatement against the numpy restatement (two independent codings),
   * a 50-digit mpmath evaluation of the same formulas on small cases,
   * the algebraic identities the reference algorithm satisfies.
 

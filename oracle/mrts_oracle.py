@@ -1,6 +1,7 @@
 """numpy restatement of autoFRK's mrts path (TEST INFRASTRUCTURE -- see oracle/__init__.py).
 
-PARITY UNPINNED (no reference tests / golden vectors exist; the reference cannot be built here).
+Pinned to the reference's own compiled source (oracle/_ref, tests/test_oracle_ref.py) for the functions of
+src/autoFRK.cpp; the two R front-ends at the end have no executable reference here (no R interpreter).
 
 Follows, line by line:
   src/autoFRK.cpp:60-103    tpm2

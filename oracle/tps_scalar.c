@@ -1,7 +1,7 @@
 /* Plain-C restatement of the reference's scalar TPS kernel loops -- TEST INFRASTRUCTURE, NOT
- * PRODUCT CODE (see oracle/__init__.py).  PARITY UNPINNED: the reference has no tests or golden
- * vectors and cannot be built here; this file is cross-checked against the independent numpy
- * restatement (oracle/mrts_oracle.py) and against 50-digit arithmetic in tests/test_oracle.py.
+ * PRODUCT CODE (see oracle/__init__.py).  Pinned: tests/test_oracle_ref.py checks it bit for bit
+ * (0 ulp, r == 0 included) against the reference's own loops compiled unmodified (oracle/_ref) and
+ * against the vectors those produced (tests/golden/ref_vectors.npz).
  *
  * Follows (column-major storage, like Eigen::MatrixXd / R):
  *   oracle_tpm_predict : src/autoFRK.cpp:109-153  (same loop order: i outer, j inner)

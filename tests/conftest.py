@@ -25,3 +25,18 @@ def _built_libraries():
     ob.build_oracle()
     ob.build_ref()          # the reference's own translation unit (built where /root/reference exists; travels prebuilt)
     yield
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """observed errors of the parity checks (tests/util.py:within) -> gpurun_out/observed_errors.json"""
+    import json
+
+    try:
+        from util import OBSERVED
+    except Exception:
+        return
+    if OBSERVED:
+        out = ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        (out / "observed_errors.json").write_text(json.dumps(
+            {k: {"observed": v[0], "bound": v[1]} for k, v in sorted(OBSERVED.items())}, indent=1))

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from util import TOL, colrel, relmax
+from util import TOL, colrel, relmax, within
 
 pytestmark = pytest.mark.gpu
 
@@ -30,15 +30,15 @@ def test_mrtsrcpp_fit(d, m, kstar):
     K = kstar + d + 1
     assert got["X"].shape == (m, K) and got["UZ"].shape == (m + d + 1, K) and got["BBBH"].shape == (d + 1, m)
     # deterministic pieces: 1e-10 or better
-    assert relmax(got["nconst"], ref["nconst"]) < 1e-13
-    assert colrel(got["BBBH"].T, ref["BBBH"].T) < TOL
-    assert colrel(got["X"][:, :d + 1], ref["X"][:, :d + 1]) < 1e-13
+    within("test_mrtsrcpp_fit:got[nconst]", relmax(got["nconst"], ref["nconst"]), 1e-13)
+    within("test_mrtsrcpp_fit:got[BBBH].T", colrel(got["BBBH"].T, ref["BBBH"].T), TOL)
+    within("test_mrtsrcpp_fit:got[X][", colrel(got["X"][:, :d + 1], ref["X"][:, :d + 1]), 1e-13)
     assert np.array_equal(got["UZ"][m:, :], ref["UZ"][m:, :])          # unit + xobs_diag block, exact
     assert np.all(got["UZ"][:m, kstar:] == 0.0)
     # eigen-columns: per column up to sign at 1e-8 (LAPACK-vs-LAPACK differences scale with 1/eigengap)
     gam_ref = ref["X"][:, d + 1:]
     gam = _sign_align(got["X"][:, d + 1:], gam_ref)
-    assert colrel(gam, gam_ref) < 1e-8
+    within("test_mrtsrcpp_fit:gam", colrel(gam, gam_ref), 1e-8)
     # invariants at 1e-10: orthonormality, orthogonality to [1, Xu], eigen-residual against the oracle's AHA
     g = got["X"][:, d + 1:] / np.sqrt(m)
     assert np.max(np.abs(g.T @ g - np.eye(kstar))) < TOL
@@ -54,7 +54,7 @@ def test_mrtsrcpp_fit(d, m, kstar):
     assert np.all(rho > 0)
     # gammas block consistent with the library's own eigenvectors: UZ = (I-P) gamma / rho * sqrt(m)
     gs = (g - B @ np.linalg.solve(B.T @ B, B.T @ g)) / rho * np.sqrt(m)
-    assert colrel(got["UZ"][:m, :kstar], gs) < 1e-9
+    within("test_mrtsrcpp_fit:got[UZ][m", colrel(got["UZ"][:m, :kstar], gs), 1e-11)   # observed 5.6e-13 on B200
 
 
 def test_identity_predict_at_knots_equals_fit():
@@ -67,12 +67,12 @@ def test_identity_predict_at_knots_equals_fit():
         obj = G.mrts(knot, K)
         assert obj.X.shape == (m, K)
         at = G.predict_mrts(obj, knot)
-        assert colrel(at, obj.X) < TOL
+        within("test_identity_predict_at_knots_equals_fit:at", colrel(at, obj.X), TOL)
         # mrts(knot, k, x) == predict(mrts(knot, k), x)
         x = rng.random((777, d))
         a = G.mrts(knot, K, x).X
         b = G.predict_mrts(obj, x)
-        assert colrel(a, b) < TOL
+        within("test_identity_predict_at_knots_equals_fit:a", colrel(a, b), TOL)
 
 
 def test_mrts_frontend_matches_oracle_subspace():
@@ -88,8 +88,8 @@ def test_mrts_frontend_matches_oracle_subspace():
     ref = O.mrts(knot, K, x)
     got = G.mrts(knot, K, x)
     assert got.X.shape == ref.X.shape == (500, K)
-    assert colrel(got.X[:, :d + 1], ref.X[:, :d + 1]) < 1e-13
-    assert colrel(_sign_align(got.X[:, d + 1:], ref.X[:, d + 1:]), ref.X[:, d + 1:]) < 1e-8
+    within("test_mrts_frontend_matches_oracle_subspace:got.X[", colrel(got.X[:, :d + 1], ref.X[:, :d + 1]), 1e-13)
+    within("test_mrts_frontend_matches_oracle_subspace:_sign_aligngot.X[", colrel(_sign_align(got.X[:, d + 1:], ref.X[:, d + 1:]), ref.X[:, d + 1:]), 1e-10)   # observed 2.9e-12 on B200
     ref0 = O.mrts(knot, K)
     got0 = G.mrts(knot, K)
     assert got0.X.shape == ref0.X.shape == (m + 7, K)   # duplicates: evaluated at all original rows
@@ -125,7 +125,7 @@ def test_getASCeigens():
     A = A.T @ A
     ref = O.getASCeigens(A)
     got = G.getASCeigens(A)
-    assert relmax(got["value"], ref["value"]) < 1e-12
+    within("test_getASCeigens:got[value]", relmax(got["value"], ref["value"]), 1e-12)
     V = got["vector"]
     assert np.max(np.abs(V.T @ V - np.eye(120))) < 1e-12
     assert np.max(np.abs(A @ V - V * got["value"])) / got["value"].max() < 1e-12
@@ -147,4 +147,4 @@ def test_rigid_motion_invariance_on_the_gpu(d):
     B = G.predict_mrts(G.mrts(Xu @ Q + shift, K), x @ Q + shift)[:, d + 1:]
     s = np.sign(np.sum(A * B, axis=0))
     err = np.max(np.max(np.abs(A * s - B), axis=0) / np.max(np.abs(B), axis=0))
-    assert err < 1e-7, err
+    within("test_rigid_motion_invariance_on_the_gpu:err", err, 1e-10)   # observed 2.3e-12 on B200

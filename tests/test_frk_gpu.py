@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from util import TOL, colrel, relmax
+from util import TOL, colrel, relmax, within
 
 pytestmark = pytest.mark.gpu
 
@@ -29,9 +29,9 @@ def test_gram_stats_matches_numpy(n, K, T):
         assert Cm is None and zz == 0.0
     else:
         Gm, Cm, zz = G.gram_stats(F, Z)
-        assert relmax(Cm, F.T @ Z) < 1e-12
+        within("test_gram_stats_matches_numpy:Cm", relmax(Cm, F.T @ Z), 1e-12)
         assert abs(zz - np.sum(Z * Z)) / np.sum(Z * Z) < 1e-13
-    assert relmax(Gm, F.T @ F) < 1e-12
+    within("test_gram_stats_matches_numpy:Gm", relmax(Gm, F.T @ F), 1e-12)
     assert np.array_equal(Gm, Gm.T)          # exactly symmetric by construction
 
 
@@ -73,7 +73,7 @@ def test_gram_dev_and_fused_predict_gram():
     _lib.check(_lib.lib.frk_plan_predict_gram_dev(plan._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(Z.data_ptr()), T, n, None,
                                                   C.c_void_p(fused.data_ptr()), 8192, st))
     torch.cuda.synchronize()
-    assert relmax(fused.cpu().numpy(), packed.cpu().numpy()) < 1e-12
+    within("test_gram_dev_and_fused_predict_gram:fused.cpu.numpy", relmax(fused.cpu().numpy(), packed.cpu().numpy()), 1e-12)
 
 
 @pytest.mark.parametrize("n,Kmax,T,s", [(6000, 60, 1, 0.0), (6000, 60, 7, 0.0), (3000, 40, 64, 0.0), (5000, 33, 5, 0.3)])
@@ -126,13 +126,13 @@ def test_cMLEimat_matches_oracle(n, K, T, s):
     got = G.cMLEimat(F, Z, s, wSave=True)
     assert abs(got["v"] - ref["v"]) <= TOL * abs(ref["v"])
     assert abs(got["negloglik"] - ref["negloglik"]) <= TOL * abs(ref["negloglik"])
-    assert relmax(got["M"], ref["M"]) < TOL
-    assert relmax(got["w"], ref["w"]) < 1e-9           # the reference's own cancellation ~ dhat/v
+    within("test_cMLEimat_matches_oracle:got[M]", relmax(got["M"], ref["M"]), TOL)
+    within("test_cMLEimat_matches_oracle:got[w]", relmax(got["w"], ref["w"]), 5e-9)           # the reference's own cancellation ~ dhat/v   # observed 4.6e-10 on B200
     # V: the literal formula is numerically unstable; strict against the closed form, loose vs literal
     Gs, Cs, zz = O.gram_stats(F, Z)
     closed = O.cmle_from_stats(Gs, Cs, zz, n, T, s=s, wSave=True)
-    assert relmax(got["V"], closed["V"]) < 1e-9
-    assert relmax(got["V"], ref["V"]) < 1e-3
+    within("test_cMLEimat_matches_oracle:got[V]_vs_closed_form", relmax(got["V"], closed["V"]), 1e-9)
+    within("test_cMLEimat_matches_oracle:got[V]_vs_literal", relmax(got["V"], ref["V"]), 5e-4)   # observed 3.0e-05 on B200: the literal V cancels
     assert np.array_equal(got["M"], got["M"].T)
     only = G.cMLEimat(F, Z, s)                         # onlylogLike = !wSave
     assert set(only) == {"negloglik"} and only["negloglik"] == got["negloglik"]
@@ -146,9 +146,9 @@ def test_getHalf_getEigen_cMLE():
     F, Z = _data(n, K, T, seed=9)
     half_ref = O.getHalf(F, F)
     half = G.getHalf(F, F)
-    assert relmax(half, half_ref) < TOL
+    within("test_getHalf_getEigen_cMLE:half", relmax(half, half_ref), TOL)
     iDF = F * np.linspace(0.5, 2.0, n)[:, None]        # a diagonal-D weighting: t(Fk) %*% iDFk path
-    assert relmax(G.getHalf(F, iDF), O.getHalf(F, iDF)) < 1e-9
+    within("test_getHalf_getEigen_cMLE:G.getHalfF", relmax(G.getHalf(F, iDF), O.getHalf(F, iDF)), 1e-13)   # observed 1.0e-15 on B200
     e_ref, e = O.getEigen(F.T @ F), G.getEigen(F.T @ F)
     assert relmax(e["value"], e_ref["value"]) < 1e-12 and np.all(np.diff(e["value"]) <= 0)
     # cMLE given half and JSJ (selectBasis' inner call, R/autoFRK.R:306-316)
@@ -161,7 +161,7 @@ def test_getHalf_getEigen_cMLE():
     r2, g2 = O.cMLE(F, T, trS, half_ref, JSJ, wSave=True), G.cMLE(F, T, trS, half_ref, JSJ, wSave=True)
     assert abs(g2["v"] - r2["v"]) <= TOL * abs(r2["v"]) and relmax(g2["M"], r2["M"]) < TOL
     assert g2["L"].shape == r2["L"].shape
-    assert relmax(g2["L"] @ g2["L"].T @ F[:, :3], r2["L"] @ r2["L"].T @ F[:, :3]) < 1e-9   # L up to column signs
+    within("test_getHalf_getEigen_cMLE:g2[L]g2[L].TF[", relmax(g2["L"] @ g2["L"].T @ F[:, :3], r2["L"] @ r2["L"].T @ F[:, :3]), 1e-13)   # L up to column signs   # observed 2.5e-15 on B200
     r3, g3 = O.cMLE(F, T, trS, half_ref, JSJ, vfixed=0.7, wSave=True), G.cMLE(F, T, trS, half_ref, JSJ, vfixed=0.7, wSave=True)
     assert g3["v"] == 0.7 and relmax(g3["M"], r3["M"]) < TOL
 
@@ -184,7 +184,7 @@ def test_sol_v_branches_through_cMLE():
         got = G.cMLE(F, 2, trS, half, JSJ, wSave=True)
         assert abs(got["v"] - ref["v"]) <= 1e-12 * max(1.0, abs(ref["v"])), (n, d)
         assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-12 * abs(ref["negloglik"])
-        assert relmax(got["M"], ref["M"]) < 1e-12
+        within("test_sol_v_branches_through_cMLE:got[M]", relmax(got["M"], ref["M"]), 1e-12)
 
 
 def test_autoFRK_config1_and_predict_FRK():
@@ -201,7 +201,7 @@ def test_autoFRK_config1_and_predict_FRK():
     got = G.autoFRK(z, loc)
     Kr, Kg = ref["G"].X.shape[1], got["G"].X.shape[1]
     assert np.array_equal(got["G"].Kgrid, ref["G"].extra["Kgrid"]) and len(got["G"].Kgrid) == 30 and got["G"].Kgrid.max() == 446
-    assert relmax(got["G"].AIC, ref["G"].extra["AIC"]) < 1e-8
+    within("test_autoFRK_config1_and_predict_FRK:got[G].AIC", relmax(got["G"].AIC, ref["G"].extra["AIC"]), 1e-11)   # observed 1.1e-13 on B200
     assert Kg == Kr
     assert abs(got["s"] - ref["s"]) <= 1e-8 * abs(ref["s"])
     assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-8 * abs(ref["negloglik"])
@@ -209,11 +209,11 @@ def test_autoFRK_config1_and_predict_FRK():
     newloc = rng.random((1500, 2))
     pr = O.predict_FRK(ref, newloc=newloc, se_report=True)
     pg = G.predict_FRK(got, newloc=newloc, se_report=True)
-    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-7
-    assert relmax(pg["se"], pr["se"]) < 1e-6
+    within("test_autoFRK_config1_and_predict_FRK:pg[pred.value]", relmax(pg["pred.value"], pr["pred.value"]), 1e-11)   # observed 4.6e-14 on B200
+    within("test_autoFRK_config1_and_predict_FRK:pg[se]", relmax(pg["se"], pr["se"]), 1e-7)   # observed 4.1e-09 on B200
     # newloc = NULL: basis <- object$G
     p0r, p0g = O.predict_FRK(ref), G.predict_FRK(got)
-    assert relmax(p0g["pred.value"], p0r["pred.value"]) < 1e-7
+    within("test_autoFRK_config1_and_predict_FRK:p0g[pred.value]", relmax(p0g["pred.value"], p0r["pred.value"]), 1e-11)   # observed 3.9e-14 on B200
 
 
 def test_autoFRK_multi_replicate_with_given_basis():
@@ -232,19 +232,19 @@ def test_autoFRK_multi_replicate_with_given_basis():
     ref = O.autoFRK(Z, loc, G=Fo)
     got = G.autoFRK(Z, loc, G=Fg)
     assert abs(got["s"] - ref["s"]) <= TOL * abs(ref["s"])
-    assert relmax(got["M"], ref["M"]) < TOL
-    assert relmax(got["w"], ref["w"]) < 1e-9
+    within("test_autoFRK_multi_replicate_with_given_basis:got[M]", relmax(got["M"], ref["M"]), TOL)
+    within("test_autoFRK_multi_replicate_with_given_basis:got[w]", relmax(got["w"], ref["w"]), 1e-9)
     newloc = rng.random((2000, 2))
     pr = O.predict_FRK(ref, newloc=newloc, se_report=True)
     pg = G.predict_FRK(got, newloc=newloc, se_report=True)
-    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-9
+    within("test_autoFRK_multi_replicate_with_given_basis:pg[pred.value]", relmax(pg["pred.value"], pr["pred.value"]), 1e-9)
     assert pg["se"].shape == pr["se"].shape == (2000, T)
     # se is checked against the closed-form V (the literal V is unstable)
     Gs, Cs, zz = O.gram_stats(Fo.X, Z)
     closed = O.cmle_from_stats(Gs, Cs, zz, n, T, wSave=True)
     B = O.predict_mrts(Fo, newloc)
     se_closed = np.sqrt(np.maximum(0, np.sum((B @ closed["V"]) * B, axis=1)))
-    assert relmax(pg["se"][:, 0], se_closed) < 1e-8
+    within("test_autoFRK_multi_replicate_with_given_basis:pg[se][", relmax(pg["se"][:, 0], se_closed), 1e-11)   # observed 5.4e-13 on B200
 
 
 def test_weighted_gram_and_cMLEsp_diagonal_D():
@@ -257,8 +257,8 @@ def test_weighted_gram_and_cMLEsp_diagonal_D():
     rng = np.random.default_rng(5)
     w = rng.random(n) + 0.25
     Gm, Cm, zz = G.gram_stats(F, Z, weights=w)
-    assert relmax(Gm, F.T @ (w[:, None] * F)) < 1e-12
-    assert relmax(Cm, F.T @ (w[:, None] * Z)) < 1e-12
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:Gm", relmax(Gm, F.T @ (w[:, None] * F)), 1e-12)
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:Cm", relmax(Cm, F.T @ (w[:, None] * Z)), 1e-12)
     assert abs(zz - np.sum(w[:, None] * Z * Z)) / zz < 1e-13
     mask = (rng.random(n) > 0.3).astype(float)             # 0/1 weights = NA mask of one replicate (R/autoFRK.R:609-615)
     Gk, Ck, _ = G.gram_stats(F, Z[:, :1], weights=mask)
@@ -275,12 +275,12 @@ def test_weighted_gram_and_cMLEsp_diagonal_D():
     got = G.cMLEsp(F, Z, D, wSave=True)
     assert abs(got["s"] - ref["s"]) <= TOL * abs(ref["s"])
     assert abs(got["negloglik"] - ref["negloglik"]) <= TOL * abs(ref["negloglik"])
-    assert relmax(got["M"], ref["M"]) < TOL
-    assert relmax(got["w"], ref["w"]) < 1e-9
-    assert relmax(got["V"], ref["V"]) < 1e-3                # literal V: catastrophic cancellation
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:got[M]", relmax(got["M"], ref["M"]), TOL)
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:got[w]", relmax(got["w"], ref["w"]), 1e-9)
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:got[V]", relmax(got["V"], ref["V"]), 2e-4)                # literal V: catastrophic cancellation   # observed 7.1e-06 on B200
     # indeMLE routes a non-constant diagonal D to cMLEsp and a constant one to cMLEimat (R/autoFRK.R:775-806)
     r1 = G.indeMLE(Z, F, D=D, wSave=True)
-    assert relmax(r1["M"], ref["M"]) < TOL
+    within("test_weighted_gram_and_cMLEsp_diagonal_D:r1[M]", relmax(r1["M"], ref["M"]), TOL)
     r2, r3 = G.indeMLE(Z, F, D=np.full(n, 2.0), wSave=True), G.indeMLE(Z, F, wSave=True)
     assert np.array_equal(r2["M"], r3["M"])
 
@@ -296,12 +296,12 @@ def test_invCz_ZinvC_getLikelihood():
     z = rng.standard_normal((n, T))
     Rd = rng.random(n) + 0.5
     got = G.invCz(Rd, L, z)
-    assert relmax(got, O.invCz(Rd, L, z)) < TOL
+    within("test_invCz_ZinvC_getLikelihood:got", relmax(got, O.invCz(Rd, L, z)), TOL)
     small = slice(0, 300)
     dense = np.linalg.solve(np.diag(Rd[small]) + L[small] @ L[small].T, z[small])
-    assert relmax(G.invCz(Rd[small], L[small], z[small]), dense) < TOL
-    assert relmax(G.invCz(0.7, L, z[:, :1]), O.invCz(np.full(n, 0.7), L, z[:, :1])) < TOL      # scalar R = s * I
-    assert relmax(G.ZinvC(Rd[small], L[small], z[small].T), O.ZinvC(np.diag(Rd[small]), L[small], z[small].T)) < TOL
+    within("test_invCz_ZinvC_getLikelihood:G.invCzRd[small]", relmax(G.invCz(Rd[small], L[small], z[small]), dense), TOL)
+    within("test_invCz_ZinvC_getLikelihood:G.invCz0.7", relmax(G.invCz(0.7, L, z[:, :1]), O.invCz(np.full(n, 0.7), L, z[:, :1])), TOL)      # scalar R = s * I
+    within("test_invCz_ZinvC_getLikelihood:G.ZinvCRd[small]", relmax(G.ZinvC(Rd[small], L[small], z[small].T), O.ZinvC(np.diag(Rd[small]), L[small], z[small].T)), TOL)
     # getLikelihood: complete data equals cMLEimat's negloglik; with NAs equals the oracle's masked evaluation
     F, Z = _data(4000, 9, 4, seed=3)
     fit = O.cMLEimat(F, Z, 0.0, wSave=True)
@@ -336,14 +336,14 @@ def test_predict_FRK_with_new_observations():
     newloc = rng.random((1200, 2))
     pr = O.predict_FRK(ref, obsData=obs, obsloc=obsloc, newloc=newloc, se_report=True)
     pg = G.predict_FRK(got, obsData=obs, obsloc=obsloc, newloc=newloc, se_report=True)
-    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-8
-    assert relmax(pg["se"], pr["se"]) < 1e-5
+    within("test_predict_FRK_with_new_observations:pg[pred.value]", relmax(pg["pred.value"], pr["pred.value"]), 1e-10)   # observed 6.9e-12 on B200
+    within("test_predict_FRK_with_new_observations:pg[se]", relmax(pg["se"], pr["se"]), 5e-6)   # observed 2.4e-07 on B200
     # obsloc = NULL: new data at the training sites
     obs2 = z.ravel() + 0.1 * rng.standard_normal(n)
     pr2 = O.predict_FRK(ref, obsData=obs2, se_report=True)
     pg2 = G.predict_FRK(got, obsData=obs2, se_report=True)
-    assert relmax(pg2["pred.value"], pr2["pred.value"]) < 1e-8
-    assert relmax(pg2["se"], pr2["se"]) < 1e-5              # V = M - (...) cancels on both sides
+    within("test_predict_FRK_with_new_observations:pg2[pred.value]", relmax(pg2["pred.value"], pr2["pred.value"]), 2e-9)   # observed 1.0e-10 on B200
+    within("test_predict_FRK_with_new_observations:pg2[se]", relmax(pg2["se"], pr2["se"]), 5e-5)              # V = M - (...) cancels on both sides   # observed 2.1e-06 on B200
     with pytest.raises(ValueError, match="Dimensions of obsloc and obsData"):
         G.predict_FRK(got, obsData=obs[:10], obsloc=obsloc)
 
@@ -363,9 +363,9 @@ def test_EM0miss_matches_oracle():
         got = G.EM0miss(F, Z, Dd, maxit=50, avgtol=1e-6, wSave=True, num_report=False, vfixed=vfix)
         assert got["niter"] == ref["niter"]
         assert abs(got["s"] - ref["s"]) <= 1e-9 * abs(ref["s"])
-        assert relmax(got["M"], ref["M"]) < 1e-8
-        assert relmax(got["w"], ref["w"]) < 1e-8
-        assert relmax(got["V"], ref["V"]) < 1e-7
+        within("test_EM0miss_matches_oracle:got[M]", relmax(got["M"], ref["M"]), 1e-12)   # observed 1.4e-14 on B200
+        within("test_EM0miss_matches_oracle:got[w]", relmax(got["w"], ref["w"]), 1e-12)   # observed 1.6e-14 on B200
+        within("test_EM0miss_matches_oracle:got[V]", relmax(got["V"], ref["V"]), 1e-10)   # observed 3.1e-12 on B200
         assert abs(got["negloglik"] - ref["negloglik"]) <= 1e-9 * abs(ref["negloglik"])
     # indeMLE dispatches data with NAs to EM0miss (R/autoFRK.R:829-841); an all-NA replicate keeps a zero column in w
     Z2 = Z.copy()
@@ -375,7 +375,7 @@ def test_EM0miss_matches_oracle():
     Zk = Z2[:, [0, 1, 3, 4, 5, 6]]
     rows = ~np.all(np.isnan(Zk), axis=1)                   # indeMLE drops never-observed rows first (R/autoFRK.R:754-770)
     ref2 = O.EM0miss(F[rows], Zk[rows], np.ones(int(rows.sum())), wSave=True)
-    assert relmax(r["M"], ref2["M"]) < 1e-8
+    within("test_EM0miss_matches_oracle:r[M]", relmax(r["M"], ref2["M"]), 1e-12)   # observed 4.3e-15 on B200
     assert np.array_equal(r["pinfo"]["pick"], np.nonzero(rows)[0])
 
 
@@ -403,7 +403,7 @@ def test_knn_imputation_and_autoFRK_with_missing_values():
     assert got["G"].X.shape == ref["G"].X.shape
     assert abs(got["s"] - ref["s"]) <= 1e-8 * abs(ref["s"])
     pr, pg = O.predict_FRK(ref, newloc=loc[:200]), G.predict_FRK(got, newloc=loc[:200])
-    assert relmax(pg["pred.value"], pr["pred.value"]) < 1e-7
+    within("test_knn_imputation_and_autoFRK_with_missing_values:pg[pred.value]", relmax(pg["pred.value"], pr["pred.value"]), 1e-11)   # observed 4.5e-13 on B200
     # method = "EM": AIC sweep and final fit through EM0miss
     gotem = G.autoFRK(z, loc, Kseq=[5, 9, 14], method="EM")
     assert gotem["G"].X.shape[1] in (5, 9, 14) and np.isfinite(gotem["negloglik"]) and gotem["w"].shape[1] == 1
@@ -449,7 +449,7 @@ def test_gram_small_K_variants(n, K, T, weighted, path, monkeypatch):
     assert relmax(G, Fh.T @ (wh[:, None] * Fh)) < 1e-12 and np.array_equal(G, G.T)
     if T:
         Cm = packed[K * K:K * K + K * T].cpu().numpy().reshape(K, T, order="F")
-        assert relmax(Cm, Fh.T @ (wh[:, None] * Zh[:, :T])) < 1e-12
+        within("test_gram_small_K_variants:Cm", relmax(Cm, Fh.T @ (wh[:, None] * Zh[:, :T])), 1e-12)
         zz = np.sum(wh[:, None] * Zh[:, :T] ** 2)
         assert abs(packed[-1].item() - zz) / zz < 1e-12
     else:
@@ -542,14 +542,14 @@ def test_cMLEimat_scale_equivariance():
     sc = G.cMLEimat(F, a * Z, 0.0, wSave=True)
     assert abs(sc["v"] - a * a * base["v"]) <= 1e-10 * sc["v"]
     assert relmax(sc["M"], a * a * base["M"]) < 1e-10 and relmax(sc["V"], a * a * base["V"]) < 1e-9
-    assert relmax(sc["w"], a * base["w"]) < 1e-10
+    within("test_cMLEimat_scale_equivariance:sc[w]", relmax(sc["w"], a * base["w"]), 1e-10)
     assert abs(sc["negloglik"] - (base["negloglik"] + n * T * np.log(a * a))) <= 1e-10 * abs(sc["negloglik"])
     c = np.random.default_rng(5).random(K) + 0.5
     rs = G.cMLEimat(np.asfortranarray(F * c), Z, 0.0, wSave=True)
     assert abs(rs["v"] - base["v"]) <= 1e-10 * base["v"]
     assert abs(rs["negloglik"] - base["negloglik"]) <= 1e-10 * abs(base["negloglik"])
-    assert relmax(rs["M"], base["M"] / np.outer(c, c)) < 1e-9
-    assert relmax(rs["w"], base["w"] / c[:, None]) < 1e-9
+    within("test_cMLEimat_scale_equivariance:rs[M]", relmax(rs["M"], base["M"] / np.outer(c, c)), 1e-13)   # observed 2.6e-15 on B200
+    within("test_cMLEimat_scale_equivariance:rs[w]", relmax(rs["w"], base["w"] / c[:, None]), 1e-13)   # observed 2.1e-15 on B200
 
 
 def test_predict_FRK_argument_contract():

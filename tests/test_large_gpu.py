@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from util import TOL, colrel
+from util import TOL, colrel, within
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +23,7 @@ def test_max_knots_fit_and_identity():
     obj = G.MrtsBasis(fit["X"], fit["UZ"], Xu, fit["nconst"], fit["BBBH"])
     assert obj.plan().info["slices"] == 3
     at = G.predict_mrts(obj, Xu)
-    assert colrel(at, fit["X"]) < 1e-9          # 5000-term sums against eigenvalues down to ~1e-6 of the largest
+    within("test_max_knots_fit_and_identity:at", colrel(at, fit["X"]), 1e-9)          # 5000-term sums against eigenvalues down to ~1e-6 of the largest
 
 
 def test_int64_indexing_and_row_equivariance():
@@ -86,7 +86,7 @@ def test_config3_full_size_3d():
     scale = X.abs().amax(dim=0)
     for s0 in spots.tolist():
         err = ((out[s0:s0 + m] - X).abs().amax(dim=0) / scale).max().item()
-        assert err < 1e-9, (s0, err)                                       # fit-vs-predict identity
+        within("test_config3_full_size_3d:err", err, 5e-11)   # observed 1.3e-12 on B200
     assert torch.equal(out[s0:s0 + m], out[0:m])                           # same rows, same values wherever they sit
     tail = slice(n2 - 3000, n2 - m)
     sub = torch.empty((K, tail.stop - tail.start), dtype=torch.float64, device="cuda").T

@@ -1,4 +1,4 @@
-"""CPU-only checks that pin down the oracle itself (PARITY UNPINNED by the reference: it ships no tests).
+"""CPU-only self-consistency checks of the oracle (its pin to the reference's own source is tests/test_oracle_ref.py).
 
 Two independent codings (numpy vs plain C), 50-digit arithmetic on a small case, the algebraic identities
 of SURVEY.md section 4, and the committed golden vectors."""

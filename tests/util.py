@@ -33,3 +33,15 @@ def make_fit(d, m, kstar, seed=0):
     xd = xobs_diag_of(Xu, m)
     fit = O.mrtsrcpp(Xu, xd, kstar)
     return Xu, xd, fit, rng
+
+
+OBSERVED = {}   # label -> (largest observed error, bound): dumped to gpurun_out/observed_errors.json by conftest.py
+
+
+def within(label, err, tol):
+    """assert err < tol, remembering the observed error: bounds are meant to sit ~10x above what is observed on the
+    hardware (profiles/observed_errors_r02.json lists them), not at a round number that merely passes."""
+    err = float(err)
+    old = OBSERVED.get(label)
+    OBSERVED[label] = (max(err, old[0]) if old else err, tol)
+    assert err < tol, (label, err, tol)
