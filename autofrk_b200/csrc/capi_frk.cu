@@ -122,9 +122,10 @@ void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, con
     if (chunk_rows <= 0) chunk_rows = default_chunk_rows(mp, K);
     chunk_rows = std::min(chunk_rows, n2);
     if (chunk_rows % 2) ++chunk_rows;  // keeps every chunk 16-byte aligned for the Gram kernel's cp.async path
-    if (plan->fchunk.n < size_t(chunk_rows) * K) plan->fchunk.alloc(size_t(chunk_rows) * K);
+    const frk::StreamGuardScope ordered(plan->guard, st);
+    plan->guard.grow(plan->fchunk, size_t(chunk_rows) * K);
     const size_t plen = frk::gram_packed_len(K, T);
-    if (plan->packed_tmp.n < plen) plan->packed_tmp.alloc(plen);
+    plan->guard.grow(plan->packed_tmp, plen);
     frk::GramWorkspace& ws = frk_capi::gram_workspace();
     int first = 1;
     for (int64_t r0 = 0; r0 < n2; r0 += chunk_rows) {

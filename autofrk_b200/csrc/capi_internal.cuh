@@ -51,6 +51,7 @@ struct frk_plan {
     size_t hstage_doubles = 0;
     // fused predict -> Gram / predict -> kriging: one basis chunk + packed partial statistics
     frk::DevBuf<double> fchunk, packed_tmp, ytmp;
+    frk::StreamGuard guard;   // orders asynchronous calls that reuse these buffers from different streams
     ~frk_plan() {
         for (int i = 0; i < 2; ++i) {
             if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);

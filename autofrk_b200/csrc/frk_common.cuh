@@ -69,6 +69,52 @@ struct DevBuf {
     }
 };
 
+// Scratch that is reused by consecutive asynchronous calls (the Gram workspace of a host thread, a plan's chunk
+// buffers) is safe only if those calls are ordered.  Calls on ONE stream are; for a caller that alternates streams the
+// guard orders them explicitly: every call waits for the event recorded at the end of the previous one when it runs
+// on another stream, and buffers are only re-allocated after that event has completed.
+struct StreamGuard {
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+    StreamGuard() = default;
+    StreamGuard(const StreamGuard&) = delete;
+    StreamGuard& operator=(const StreamGuard&) = delete;
+    ~StreamGuard() {
+        if (ev) cudaEventDestroy(ev);
+    }
+    void enter(cudaStream_t st) {
+        if (used && st != last) FRK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    }
+    void leave(cudaStream_t st) {
+        if (!ev) FRK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        FRK_CUDA(cudaEventRecord(ev, st));
+        last = st;
+        used = true;
+    }
+    void quiesce() {   // before a buffer that queued work may still use is released
+        if (used) FRK_CUDA(cudaEventSynchronize(ev));
+    }
+    template <typename T>
+    void grow(DevBuf<T>& b, size_t need) {
+        if (b.n < need) {
+            quiesce();
+            b.alloc(need);
+        }
+    }
+};
+struct StreamGuardScope {
+    StreamGuard& g;
+    cudaStream_t st;
+    StreamGuardScope(StreamGuard& g_, cudaStream_t st_) : g(g_), st(st_) { g.enter(st); }
+    ~StreamGuardScope() {
+        try {
+            g.leave(st);
+        } catch (...) {
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // device primitives
 // ---------------------------------------------------------------------------------------------

@@ -272,6 +272,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     int dev = 0, sms = 0;
     FRK_CUDA(cudaGetDevice(&dev));
     FRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const StreamGuardScope ordered(ws.guard, st);
 
     const char* const path_c = std::getenv("FRK_GRAM_PATH");   // tuning / test aid: mid | narrow | tma | cpasync (default: best fit)
     const std::string path_env(path_c ? path_c : "");
@@ -289,7 +290,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
     }
 
     const int nzz = 512;
-    if (ws.zzpart.n < size_t(nzz)) ws.zzpart.alloc(nzz);
+    ws.guard.grow(ws.zzpart, size_t(nzz));
     if (T > 0) {
         const int gy = std::min(T, 32), gx = nzz / gy;   // gx * gy <= nzz partials; the rest stay zero
         if (gx * gy < nzz) FRK_CUDA(cudaMemsetAsync(ws.zzpart.p + gx * gy, 0, sizeof(double) * (nzz - gx * gy), st));
@@ -332,7 +333,7 @@ void gram_stats_dev(const double* dF, int64_t n, int K, int64_t ldf, const doubl
         a.nsplit = best_ns;
         a.rows_per_split = ((n + a.nsplit - 1) / a.nsplit + KR - 1) / KR * KR;
         const size_t need = size_t(a.nsplit) * a.npairs * TB * TB;
-        if (ws.partial.n < need) ws.partial.alloc(need);
+        ws.guard.grow(ws.partial, need);
         a.partial = ws.partial.p;
         const bool aligned = (reinterpret_cast<uintptr_t>(dF) % 16 == 0) && (ldf % 2 == 0) &&
                              (T == 0 || ((reinterpret_cast<uintptr_t>(dZ) % 16 == 0) && (ldz % 2 == 0)));

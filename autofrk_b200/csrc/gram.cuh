@@ -47,6 +47,7 @@ struct GramWorkspace {
     int mid_K = -1, mid_T = -1, mid_ntiles = 0, mid_nsets = 0, mid_kb = 0, mid_nblocks = 0;
     bool mid_ok = false;
     const char* last_path = "";
+    StreamGuard guard;       // orders calls that reuse this workspace from different streams
 };
 
 // number of doubles in the packed result [G (K x K, column-major, full symmetric) | C (K x T) | zz]

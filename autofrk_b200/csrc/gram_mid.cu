@@ -481,6 +481,7 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
         ws.mid_T = T;
         if (ws.mid_ok) {
             const size_t ub = sizeof(GramMidUnit) * MNW * MNU, tb = sizeof(GramMidTile) * P.tiles.size();
+            ws.guard.quiesce();
             ws.mid_tab.alloc((ub + tb + 7) / 8);
             FRK_CUDA(cudaMemcpyAsync(ws.mid_tab.p, P.units, ub, cudaMemcpyHostToDevice, st));
             FRK_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ws.mid_tab.p) + ub, P.tiles.data(), tb, cudaMemcpyHostToDevice, st));
@@ -517,7 +518,7 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     a.rows_cta = ((n + grid - 1) / grid + MKR - 1) / MKR * MKR;
     a.units = reinterpret_cast<const GramMidUnit*>(ws.mid_tab.p);
     const size_t need = size_t(grid) * MNW * MNU * 8 * 64 + size_t(grid);
-    if (ws.partial.n < need) ws.partial.alloc(need);
+    ws.guard.grow(ws.partial, need);
     a.partial = ws.partial.p;
     a.zzcta = ws.partial.p + size_t(grid) * MNW * MNU * 8 * 64;
 

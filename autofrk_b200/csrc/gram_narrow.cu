@@ -193,7 +193,7 @@ void launch_narrow(const NarrowArgs& a0, int sms, GramWorkspace& ws, int K, int 
     const int64_t nwarps = int64_t(grid) * NWARPS_N;
     a.rows_per_warp = std::max<int64_t>(16, ((a.n + nwarps - 1) / nwarps + 15) / 16 * 16);
     const size_t need = size_t(grid) * TI::NT * 64;
-    if (ws.partial.n < need) ws.partial.alloc(need);
+    ws.guard.grow(ws.partial, need);
     a.partial = ws.partial.p;
     if (a.w) gram_narrow_kernel<MT, NZ, true><<<grid, NTHREADS_N, smem, st>>>(a);
     else gram_narrow_kernel<MT, NZ, false><<<grid, NTHREADS_N, smem, st>>>(a);

@@ -537,6 +537,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
             }
         }
         const size_t bytes = sizeof(GramJob) * dj.size() + sizeof(unsigned);
+        ws.guard.quiesce();
         ws.pair_order.alloc((bytes + sizeof(int) - 1) / sizeof(int));
         FRK_CUDA(cudaMemcpyAsync(ws.pair_order.p, dj.data(), sizeof(GramJob) * dj.size(), cudaMemcpyHostToDevice, st));
         FRK_CUDA(cudaStreamSynchronize(st));  // `dj` is a host temporary; only on a shape change
@@ -579,7 +580,7 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     }
     a.nitems = a.nsplit * a.njobs;
     const size_t need = size_t(a.nitems) * NWARPS * TILE_DOUBLES;
-    if (ws.partial.n < need) ws.partial.alloc(need);
+    ws.guard.grow(ws.partial, need);
     a.partial = ws.partial.p;
 
     const CUtensorMap tmF = make_map(dF, n, K, ldf);

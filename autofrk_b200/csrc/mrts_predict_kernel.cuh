@@ -13,6 +13,11 @@
 //       - one TMA bulk copy (cp.async.bulk -> UBLKCP) per chunk stages W, tracked by an mbarrier,
 //         NSTAGE deep, refilled by whichever warp is last to finish with a stage,
 //       - every B-fragment load is a contiguous, conflict-free 256 B LDS.64 per warp.
+//     (The shared-memory bank conflicts ncu counts on this kernel -- 2.69e9 excess wavefronts on the bench launch --
+//     are not fragment loads: 92% of them sit on ONE instruction, the LDS.128 gather of the d = 2 log table
+//     (phi2_table: a data-dependent index per lane, ~6 excess wavefronts per warp instruction), the rest on the Phi
+//     stores; profiles/k1_r02_source_ncu_summary.txt.  The shared-memory pipe runs at 29% of its peak, so they are
+//     not on the critical path; a gather from a 16 KB table cannot be conflict-free.)
 //   * The FP64 ALU and the DMMA unit share one pipe on B200 (measured: profiles/fp64_peaks_r01.json),
 //     so kernel evaluation is pure overhead on the binding resource.  Every thread therefore
 //     evaluates the same number of Phi values for chunk c+1 INSIDE the DMMA block of chunk c (one

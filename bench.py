@@ -243,6 +243,23 @@ def measure_dmma_peak():
     return float(t.value)
 
 
+def host_copy_bandwidth(threads):
+    """payload GB/s of plain host memcpy on this box with `threads` threads (numpy copies release the GIL): the ceiling
+    of anything that has to land in pageable host memory, and what N processes share at N GPUs."""
+    n = 1 << 25                                               # 256 MB per thread
+    src = [np.ones(n) for _ in range(threads)]
+    dst = [np.empty(n) for _ in range(threads)]
+
+    def cp(i):
+        dst[i][:] = src[i]
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(cp, range(threads)))                      # touch the pages
+        t0 = time.perf_counter()
+        list(ex.map(cp, range(threads)))
+        dt = time.perf_counter() - t0
+    return threads * n * 8 / dt / 1e9
+
+
 def measured_peaks():
     try:
         return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -382,8 +399,12 @@ def main_gpu(args):
                                       "unmodified)" if kind == "ref+port" else "scalar C restatement of src/autoFRK.cpp:109-153")
                                    + ", one row block per thread, + OpenBLAS GEMM for the projection",
                          "single_thread": run_cpu_single_thread(100_000)}
+            host_bw = {"one_thread_gbs": host_copy_bandwidth(1), "all_threads_gbs": host_copy_bandwidth(threads), "threads": threads,
+                       "note": "payload rate of plain host memcpy on this box: what the D2H of an n2 x K basis lands in; N processes "
+                               "share it at N GPUs"}
         else:
             cpu_block = {"value": None, "unit": UNIT, "cores": threads, "kind": "ref+port", "sample": "timed at N=1 only"}
+            host_bw = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -414,7 +435,7 @@ def main_gpu(args):
                     "pageable": {"value": e2e_page, "unit": UNIT, "matches_pinned": same_page,
                                  "note": "pageable host buffers, as R hands them to .Call: staged through the plan's pinned "
                                          "ring + host scatter threads"},
-                    "fused": fused},
+                    "fused": fused, "host_memcpy": host_bw},
             "gpu_launches": int(launches),
             "clocks": summarize_clocks(samples),
         }

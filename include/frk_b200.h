@@ -16,10 +16,11 @@
  * There is no CPU fallback: without a CUDA device every compute entry point fails with FRK_ECUDA.
  *
  * Concurrency: the library is safe to call from several host threads at once (per-thread handles, workspaces and
- * default stream; a device-memory cache behind a mutex).  Within ONE host thread, and for ONE plan object, calls
- * must be issued on one stream at a time: the Gram workspace (one per host thread and device) and a plan's chunk
- * buffers are reused by consecutive calls without cross-stream ordering.  Two streams -> two host threads (and two
- * plans), or wait for the first call's stream before issuing on the second.
+ * default stream; a device-memory cache behind a mutex).  Scratch that consecutive `_dev` calls reuse (the Gram
+ * workspace of a host thread, a plan's chunk buffers) is ordered across streams by events: a call issued on another
+ * stream than the previous one first waits for that call's completion event, and buffers are only re-allocated after
+ * it.  So one thread may alternate streams freely; what it gains from several streams is ordering flexibility, not
+ * overlap of two calls that share a workspace -- use two host threads (and two plans) for that.
  * Limits: dimensions are int64_t / int32_t as declared; n2 < 2^31 rows per call for the TMA-staged Gram kernels
  * (larger inputs take the cp.async kernel); knots m <= 65535 (the reference caps them at maxknot = 5000).
  */

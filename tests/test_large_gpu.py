@@ -192,3 +192,69 @@ def test_bitwise_repeatability():
     a, b = plan.predict_dev(x), plan.predict_dev(x)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_two_host_threads_and_two_streams():
+    """Concurrency contract of include/frk_b200.h: (i) two host threads drive the library at once (per-thread handles,
+    workspaces, default stream) and get exactly the results of serial calls; (ii) one thread alternating two streams on
+    the same workspace / plan is ordered by the library's events -- results equal the single-stream ones bit for bit."""
+    import ctypes as C
+    import threading
+
+    import torch
+    from autofrk_b200 import _lib, frk as GF, mrts as G
+
+    rng = np.random.default_rng(21)
+    jobs = []
+    for seed, (m, K, n, T) in enumerate([(150, 40, 60_000, 3), (220, 90, 45_000, 1)]):
+        knot = rng.random((m, 2))
+        x = rng.random((n, 2))
+        Z = rng.standard_normal((n, T))
+        jobs.append((knot, K, x, Z))
+
+    def work(job, out, idx, reps):
+        knot, K, x, Z = job
+        for _ in range(reps):
+            obj = G.mrts(knot, K)                       # device fit (cuSOLVER, K x K stage on this thread's default stream)
+            B = G.predict_mrts(obj, x)
+            fit = GF.cMLEimat(B, Z, 0.0, wSave=True)
+            out[idx] = (B, fit["M"], fit["w"], fit["v"])
+
+    serial = [None, None]
+    for i, job in enumerate(jobs):
+        work(job, serial, i, 1)
+    par = [None, None]
+    th = [threading.Thread(target=work, args=(job, par, i, 3)) for i, job in enumerate(jobs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for s, p in zip(serial, par):
+        assert np.array_equal(s[0], p[0]) and np.array_equal(s[1], p[1]) and np.array_equal(s[2], p[2]) and s[3] == p[3]
+
+    # (ii) two streams, one thread, one workspace
+    n, K, T = 300_000, 64, 4
+    g = torch.Generator(device="cuda").manual_seed(4)
+    F = torch.randn((K, n), dtype=torch.float64, device="cuda", generator=g).T
+    Zt = torch.randn((T, n), dtype=torch.float64, device="cuda", generator=g).T
+    plen = _lib.lib.frk_gram_packed_len(K, T)
+    ref = torch.empty(plen, dtype=torch.float64, device="cuda")
+    st0 = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def gram(rows, out, st):
+        _lib.check(_lib.lib.frk_gram_stats_dev(C.c_void_p(F.data_ptr()), rows, K, n, C.c_void_p(Zt.data_ptr()), T, n, None,
+                                               C.c_void_p(out.data_ptr()), st))
+    refs = []
+    for rows in (n, n // 2, n // 3):
+        r = torch.empty(plen, dtype=torch.float64, device="cuda")
+        gram(rows, r, st0)
+        torch.cuda.synchronize()
+        refs.append(r.clone())
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [torch.empty(plen, dtype=torch.float64, device="cuda") for _ in range(6)]
+    torch.cuda.synchronize()
+    for k in range(6):                                   # back to back, alternating streams, no host synchronisation
+        gram((n, n // 2, n // 3)[k % 3], outs[k], C.c_void_p((s1 if k % 2 == 0 else s2).cuda_stream))
+    torch.cuda.synchronize()
+    for k in range(6):
+        assert torch.equal(outs[k], refs[k % 3]), k
