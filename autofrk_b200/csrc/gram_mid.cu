@@ -12,17 +12,17 @@
 //   * the host deals the units to warps (two per warp), longest first, onto the least loaded sub-partition.  When
 //     the units fit 8 (4) warps the 16 warps form 2 (4) SETS that take alternate row stages with the same unit
 //     table, rotated across sub-partitions, so the pipe load is equal by construction;
-//   * rows arrive as for the wide kernel: cp.async.bulk.tensor.2d boxes of [32 columns][16 rows] with SWIZZLE_128B
-//     (conflict-free fragment LDS.64 under the permuted k order), 32 rows per stage, a ring of up to 12 stages,
-//     `full` mbarriers, last-finisher re-arm, no CTA barrier in the loop; ragged rows / columns are zero-filled by
-//     the TMA unit.  Staging alternatives were measured and dropped (tools/tma_stream_bench.cu,
-//     profiles/tma_stream_bench_r02.json, profiles/gram_probe_r02_v3..v6): one CTA per SM streaming this column-major
-//     pattern with such boxes and no arithmetic reaches 3.6 TB/s (32-row stages) to 4.9 TB/s (128-row stages, row
-//     boxes of a column block issued together) against 7.0 TB/s for a plain LDG.128 read; per-column 1-D bulk
-//     copies cost >= 65 clocks each and need 2 KB per copy (two 75 KB stages: too coarse a ring once the arithmetic
-//     holds a stage -- 3.5 TB/s with a 14-clock-per-row hold); cp.async from the warp that re-arms a stage puts
-//     18 .. 72 LDGSTS on the ring's critical path (2x slower); 64 / 128-row stages made every set wait for whole
-//     stages and lost more than the longer runs gained;
+//   * staging: one cp.async.bulk.tensor.2d box of [32 columns][36 rows], NOT swizzled, per column block and 32-row
+//     stage.  The four extra rows are never read: they make the column pitch 36 doubles == 4 (mod 16), so the fragment
+//     LDS.64 of a shared-memory phase (columns g = 0..3 x rows t = 0..3 of a k4-step, natural k order) fall on 16
+//     different banks without any swizzle.  Why not the wide kernel's SWIZZLE_128B boxes of 16 rows: the TMA unit's
+//     cost is per box ROW -- one CTA per SM streaming this column-major pattern with no arithmetic reaches 3.3-4.7 TB/s
+//     with 128-byte rows against 6.4-7.2 TB/s with 256..544-byte rows (7.0 TB/s for a plain LDG.128 read;
+//     tools/tma_stream_bench.cu, profiles/tma_stream_bench_r02.json).  A ring of up to 12 stages, `full` mbarriers,
+//     last-finisher re-arm, no CTA barrier in the loop; ragged rows / columns are zero-filled by the TMA unit.
+//     Also measured and dropped (profiles/gram_probe_r02_v3..v6): per-column 1-D bulk copies (>= 65 clocks each: need
+//     2 KB per copy, and then two 75 KB stages are too coarse a ring), cp.async issued by the warp that re-arms a stage
+//     (18..72 LDGSTS on the ring's critical path: 2x slower), 64/128-row stages shared by all sets (-8..-40%);
 //   * zz is accumulated from the Z boxes already in shared memory by one warp of the stage's set (in rotation);
 //   * one persistent CTA per SM owns a contiguous row range; partial tiles go to a workspace and a second kernel
 //     adds them in a fixed order (bitwise reproducible) and mirrors G.
@@ -41,17 +41,18 @@ namespace frk {
 namespace {
 
 constexpr int MCB = 32;                    // columns per staged block
-constexpr int MBOXR = 16;                  // rows per TMA box (the 128-byte swizzle span)
+constexpr int MBOXR = 36;                  // rows per TMA box: the stage's 32 plus 4 that only pad the column pitch
 constexpr int MKR = 32;                    // rows per stage
 constexpr int MKQ = MKR / 4;               // k4-steps per stage
-constexpr int MBOX_BYTES = MCB * MBOXR * 8;          // 4 KB
-constexpr int MSLOT_BYTES = MCB * MKR * 8;           // 8 KB: one column block of one stage
+constexpr int MPITCH = MBOXR * 8;                     // bytes between columns of a staged block: 36 doubles == 4 (mod 16)
+constexpr int MGROUP_BYTES = 8 * MPITCH;             // one 8-column group
+constexpr int MSLOT_BYTES = MCB * MPITCH;            // 9 KB: one column block of one stage = one TMA box
 constexpr int MNW = GRAM_MID_WARPS;
 constexpr int MNT = MNW * 32;
 constexpr int MNU = GRAM_MID_UNITS;        // units per warp
 constexpr int MAXBLK = 8;
 constexpr int MAXST = 12;
-constexpr size_t MID_SMEM_BUDGET = 200 * 1024;
+constexpr size_t MID_SMEM_BUDGET = 222 * 1024;   // eight 27 KB stages (three column blocks) must fit
 
 struct MidArgs {
     int K, T, kb, nblocks, nst, nsets, ntiles;
@@ -83,19 +84,19 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // All k4-steps of one stage for one unit of shape NR x NC (TRI: without tile (1,0)), in one basic block, so the loads
 // of the next k4-step are scheduled under the DMMAs of this one.  Every fragment address is a register + immediate.
 template <int NR, int NC, bool TRI, bool WEIGHTED>
-__device__ __forceinline__ void mid_unit(uint32_t As, const int (&off)[4], int ab, int bb, double (&acc)[2][4][2],
+__device__ __forceinline__ void mid_unit(uint32_t As, int lane_off, int ab, int bb, double (&acc)[2][4][2],
                                          const double* __restrict__ w, int64_t r0, int64_t r_end, int t) {
 #pragma unroll
     for (int q = 0; q < MKQ; ++q) {
-        const uint32_t pa = As + ab + off[q & 3] + (q >> 2) * MBOX_BYTES;
-        const uint32_t pb = As + bb + off[q & 3] + (q >> 2) * MBOX_BYTES;
+        const uint32_t pa = As + ab + lane_off + q * 32;       // rows 4q + t of this lane's column
+        const uint32_t pb = As + bb + lane_off + q * 32;
         double af[NR], bf[NC];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) af[i] = lds_f64(pa + i * 1024);
+        for (int i = 0; i < NR; ++i) af[i] = lds_f64(pa + i * MGROUP_BYTES);
 #pragma unroll
-        for (int j = 0; j < NC; ++j) bf[j] = lds_f64(pb + j * 1024);
+        for (int j = 0; j < NC; ++j) bf[j] = lds_f64(pb + j * MGROUP_BYTES);
         if (WEIGHTED) {
-            const int64_t r = r0 + MBOXR * (q >> 2) + 2 * (q & 3) + (t & 1) + 8 * (t >> 1);
+            const int64_t r = r0 + 4 * q + t;
             const double wv = (r < r_end) ? __ldg(w + r) : 0.0;
 #pragma unroll
             for (int i = 0; i < NR; ++i) af[i] *= wv;
@@ -109,12 +110,12 @@ __device__ __forceinline__ void mid_unit(uint32_t As, const int (&off)[4], int a
 }
 
 template <bool WEIGHTED>
-__device__ __forceinline__ void mid_unit_dispatch(int kind, uint32_t As, const int (&off)[4], int ab, int bb,
+__device__ __forceinline__ void mid_unit_dispatch(int kind, uint32_t As, int lane_off, int ab, int bb,
                                                   double (&acc)[2][4][2], const double* __restrict__ w, int64_t r0,
                                                   int64_t r_end, int t) {
     switch (kind) {   // warp-uniform
 #define FRK_MID_CASE(id, NR, NC, TRI) \
-    case id: mid_unit<NR, NC, TRI, WEIGHTED>(As, off, ab, bb, acc, w, r0, r_end, t); break;
+    case id: mid_unit<NR, NC, TRI, WEIGHTED>(As, lane_off, ab, bb, acc, w, r0, r_end, t); break;
         FRK_MID_CASE(1, 1, 1, false) FRK_MID_CASE(2, 1, 2, false) FRK_MID_CASE(3, 1, 3, false) FRK_MID_CASE(4, 1, 4, false)
         FRK_MID_CASE(5, 2, 1, false) FRK_MID_CASE(6, 2, 2, false) FRK_MID_CASE(7, 2, 3, false) FRK_MID_CASE(8, 2, 4, false)
         FRK_MID_CASE(GRAM_MID_TRI24, 2, 4, true) FRK_MID_CASE(GRAM_MID_TRI22, 2, 2, true)
@@ -175,8 +176,8 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
     const int64_t r_end = min(a.n, r_begin + a.rows_cta);
     const int nsteps = (r_end > r_begin) ? int((r_end - r_begin + MKR - 1) / MKR) : 0;
 
-    // the box this lane copies when its warp arms a stage: lane -> (block, 16-row half)
-    const int my_blk = lane >> 1, my_half = lane & 1;
+    // the box this lane copies when its warp arms a stage: lane -> column block (one 36-row x 32-column box each)
+    const int my_blk = lane;
     const bool my_isz = my_blk >= a.kb;
     const CUtensorMap* const my_tm = my_isz ? &tmZ : &tmF;
     const int my_col = (my_isz ? my_blk - a.kb : my_blk) * MCB;
@@ -185,17 +186,15 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
         if (lane == 0) mbar_expect_tx(&full[slot], stage_tx);
         __syncwarp();
         if (my_blk < a.nblocks)
-            mid_tma_load_2d(base + size_t(slot) * stage_bytes + my_blk * MSLOT_BYTES + my_half * MBOX_BYTES, my_tm,
-                            int(r_begin + int64_t(step) * MKR) + my_half * MBOXR, my_col, &full[slot]);
+            mid_tma_load_2d(base + size_t(slot) * stage_bytes + my_blk * MSLOT_BYTES, my_tm,
+                            int(r_begin + int64_t(step) * MKR), my_col, &full[slot]);
     };
     if (warp == 0)
         for (int i = 0; i < a.nst && i < nsteps; ++i) issue(i, i);
 
-    // byte offset of this lane's fragment element inside a box for k4-step q (row 2q' + (t&1) + 8(t>>1) of column g;
-    // the 16-byte chunk index is XOR-swizzled with the column's index mod 8 == g)
-    int off[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) off[q] = g * 128 + ((((q + 4 * (t >> 1)) ^ g) << 4) + (t & 1) * 8);
+    // byte offset of this lane's fragment element inside an 8-column group: column g, row t of a k4-step (rows 4q + t;
+    // with a pitch of 36 doubles the 16 lanes of a shared-memory phase, g = 0..3 x t = 0..3, fall on 16 different banks)
+    const int lane_off = g * MPITCH + t * 8;
 
     double acc[MNU][2][4][2];
 #pragma unroll
@@ -215,15 +214,14 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
             const unsigned char* As = base + size_t(slot) * stage_bytes;
 #pragma unroll
             for (int u = 0; u < MNU; ++u)
-                mid_unit_dispatch<WEIGHTED>(kd[u], smem_u32(As), off, ab[u], bb[u], acc[u], a.w, r_begin + int64_t(step) * MKR, r_end, t);
+                mid_unit_dispatch<WEIGHTED>(kd[u], smem_u32(As), lane_off, ab[u], bb[u], acc[u], a.w, r_begin + int64_t(step) * MKR, r_end, t);
             if (a.T > 0 && duty % nact == myrank) {
                 // 16-byte chunks (two rows) of the Z boxes: chunk e -> column e / 16, row pair e % 16
                 const int nchunks = a.T * (MKR / 2);
                 for (int e = lane; e < nchunks; e += 32) {
                     const int c = e / (MKR / 2), rp = e % (MKR / 2);
                     const int blk = a.kb + c / MCB, cc = c % MCB;
-                    const double2 v = *reinterpret_cast<const double2*>(As + blk * MSLOT_BYTES + (rp >> 3) * MBOX_BYTES + cc * 128 +
-                                                                        (((rp & 7) ^ (cc & 7)) << 4));
+                    const double2 v = *reinterpret_cast<const double2*>(As + blk * MSLOT_BYTES + cc * MPITCH + rp * 16);
                     if (WEIGHTED) {
                         const int64_t r = r_begin + int64_t(step) * MKR + 2 * rp;
                         const double w0 = (r < r_end) ? __ldg(a.w + r) : 0.0, w1 = (r + 1 < r_end) ? __ldg(a.w + r + 1) : 0.0;
@@ -337,7 +335,7 @@ CUtensorMap mid_make_map(const double* ptr, int64_t rows, int cols, int64_t ld) 
     cuuint32_t box[2] = {MBOXR, MCB};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = mid_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(3, "cuTensorMapEncodeTiled failed (%d)", int(r));
     return tm;
@@ -359,8 +357,8 @@ bool gram_mid_plan(int K, int T, GramMidPlan& P) {
         U x{};
         x.ga0 = ga0; x.isz = isz; x.gb0 = gb0;
         x.u.ga0 = ga0; x.u.gb0 = gb0; x.u.isz = isz ? 1 : 0;
-        x.u.a_base = (ga0 / 4) * MSLOT_BYTES + (ga0 % 4) * 1024;
-        x.u.b_base = ((isz ? kb : 0) + gb0 / 4) * MSLOT_BYTES + (gb0 % 4) * 1024;
+        x.u.a_base = (ga0 / 4) * MSLOT_BYTES + (ga0 % 4) * MGROUP_BYTES;
+        x.u.b_base = ((isz ? kb : 0) + gb0 / 4) * MSLOT_BYTES + (gb0 % 4) * MGROUP_BYTES;
         x.u.kind = kind ? kind : 1 + (nr - 1) * 4 + (nc - 1);
         x.cost = kind == GRAM_MID_TRI24 ? 7 : (kind == GRAM_MID_TRI22 ? 3 : nr * nc);
         units.push_back(x);

@@ -25,15 +25,15 @@ __device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* tm, int c0, 
                  ::"r"(s32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(s32(bar)) : "memory");
 }
 
-struct Args { int ncols, boxc, rows_stage, nst; long long n, rows_cta; int hold_per_row; int row_fastest; };
+struct Args { int ncols, boxc, rows_stage, nst; long long n, rows_cta; int hold_per_row; int row_fastest; int boxr; };
 
 // one warp does everything: arm all stages, then wait / re-arm round robin
 __global__ void __launch_bounds__(32, 1) stream_kernel(const __grid_constant__ CUtensorMap tm, const Args a, double* sink) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     const int nboxc = (a.ncols + a.boxc - 1) / a.boxc;          // boxes across the columns
-    const int nboxr = a.rows_stage / 16;                         // boxes down the rows of a stage
-    const int box_bytes = a.boxc * 16 * 8;
+    const int nboxr = a.rows_stage >= a.boxr ? a.rows_stage / a.boxr : 1;   // boxes down the rows of a stage (a box may overlap the next stage)
+    const int box_bytes = a.boxc * a.boxr * 8;
     const int stage_bytes = nboxc * nboxr * box_bytes;
     uint64_t* full = (uint64_t*)(base + (size_t)a.nst * stage_bytes);
     const int lane = threadIdx.x;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(32, 1) stream_kernel(const __grid_constant__ C
         for (int b = lane; b < nboxc * nboxr; b += 32) {
             const int rb = a.row_fastest ? b % nboxr : b / nboxc, cb = a.row_fastest ? b / nboxr : b % nboxc;
             tma2d(base + (size_t)slot * stage_bytes + (size_t)(rb * nboxc + cb) * box_bytes, &tm,
-                  (int)(r_begin + (long long)step * a.rows_stage) + rb * 16, cb * a.boxc, &full[slot]);
+                  (int)(r_begin + (long long)step * a.rows_stage) + rb * a.boxr, cb * a.boxc, &full[slot]);
         }
     };
     for (int i = 0; i < a.nst && i < nsteps; ++i) issue(i, i);
@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(32, 1) stream_kernel(const __grid_constant__ C
     for (int step = 0; step < nsteps; ++step) {
         while (!mbar_try(&full[slot], par)) {}
         acc += *(const double*)(base + (size_t)slot * stage_bytes + lane * 8);
+        if (a.hold_per_row > 0) {
+            const long long t0 = clock64(), dt = (long long)a.hold_per_row * a.rows_stage;
+            while (clock64() - t0 < dt) {}
+        }
         __syncwarp();
         if (step + a.nst < nsteps) issue(slot, step + a.nst);
         if (++slot == a.nst) { slot = 0; par ^= 1u; }
@@ -165,66 +169,33 @@ int main() {
     const size_t budget = 200 * 1024;
     printf("[\n");
     bool first = true;
-    for (int ncols : {36, 68}) {
-        for (int boxc : {8, 32}) {
-          for (int rowfast : {0, 1})
-            for (int rows_stage : {32, 64, 128, 256}) {
-                Args a;
-                a.ncols = ncols; a.boxc = boxc; a.rows_stage = rows_stage; a.n = n; a.hold_per_row = 0; a.row_fastest = rowfast;
-                const int nboxc = (ncols + boxc - 1) / boxc;
-                const size_t stage_bytes = (size_t)nboxc * (rows_stage / 16) * boxc * 16 * 8;
-                a.nst = (int)(budget / stage_bytes);
-                if (a.nst < 2) continue;
-                if (a.nst > 24) a.nst = 24;
-                a.rows_cta = ((n + sms - 1) / sms + rows_stage - 1) / rows_stage * rows_stage;
-                CUtensorMap tm;
-                cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)ncols};
-                cuuint64_t gstr[1] = {(cuuint64_t)n * 8};
-                cuuint32_t box[2] = {16, (cuuint32_t)boxc};
-                cuuint32_t estr[2] = {1, 1};
-                if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-                    fprintf(stderr, "encode failed\n");
-                    return 1;
-                }
-                const size_t smem = (size_t)a.nst * stage_bytes + 1024 + 24 * 8 + 64;
-                cudaEvent_t e0, e1;
-                CK(cudaEventCreate(&e0));
-                CK(cudaEventCreate(&e1));
-                float best = 1e9f;
-                for (int rep = 0; rep < 4; ++rep) {
-                    CK(cudaEventRecord(e0));
-                    stream_kernel<<<sms, 32, smem>>>(tm, a, sink);
-                    CK(cudaEventRecord(e1));
-                    CK(cudaEventSynchronize(e1));
-                    float ms;
-                    CK(cudaEventElapsedTime(&ms, e0, e1));
-                    if (rep > 0 && ms < best) best = ms;
-                }
-                CK(cudaGetLastError());
-                printf("%s{\"mode\": \"tensor2d\", \"row_fastest\": %d, \"ncols\": %d, \"box_cols\": %d, \"rows_per_stage\": %d, \"stages\": %d, \"smem_in_flight_kb\": %.1f, \"ms\": %.4f, \"gbs\": %.1f}",
-                       first ? "" : ",\n", rowfast, ncols, boxc, rows_stage, a.nst, a.nst * stage_bytes / 1024.0, best,
-                       8.0 * n * ncols / best / 1e6);
-                first = false;
-                fflush(stdout);
-            }
-        }
-    }
-
-    CK(cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    // hold = clocks of arithmetic per row the real kernel would spend (14 at K = 32, T = 4); threads = warps polling
-    for (int ncols : {36})
-        for (int hold : {0, 14})
-            for (int threads : {32})
-                for (int rows_stage : {64, 128, 256}) {
-                    const int mode = 0;
+    // 2-D boxes: swizzled 16-row boxes (what the Gram kernels use) against unswizzled boxes with longer inner extent
+    for (int ncols : {36, 68})
+        for (int boxr : {16, 32, 36, 64, 68})
+            for (int hold : {0, 14})
+                for (int rows_stage : {32, 64}) {
+                    if (rows_stage < boxr - 4) continue;
+                    if ((boxr == 36 && rows_stage != 32) || (boxr == 68 && rows_stage != 64)) continue;
+                    const int boxc = 32, rowfast = 1;
                     Args a;
-                    a.ncols = ncols; a.boxc = 0; a.rows_stage = rows_stage; a.n = n; a.hold_per_row = hold; a.row_fastest = 0;
-                    const size_t stage_bytes = (size_t)ncols * (rows_stage * 8 + 32);
+                    a.ncols = ncols; a.boxc = boxc; a.rows_stage = rows_stage; a.n = n; a.hold_per_row = hold; a.row_fastest = rowfast; a.boxr = boxr;
+                    const int nboxc = (ncols + boxc - 1) / boxc;
+                    const size_t stage_bytes = (size_t)nboxc * (boxr > rows_stage ? boxr : rows_stage) * boxc * 8;
                     a.nst = (int)(budget / stage_bytes);
                     if (a.nst < 2) continue;
                     if (a.nst > 24) a.nst = 24;
-                    a.rows_cta = (n / sms) / rows_stage * rows_stage;
+                    a.rows_cta = ((n + sms - 1) / sms + rows_stage - 1) / rows_stage * rows_stage;
+                    CUtensorMap tm;
+                    cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)ncols};
+                    cuuint64_t gstr[1] = {(cuuint64_t)n * 8};
+                    cuuint32_t box[2] = {(cuuint32_t)boxr, (cuuint32_t)boxc};
+                    cuuint32_t estr[2] = {1, 1};
+                    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            boxr == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+                        fprintf(stderr, "encode failed boxr %d\n", boxr);
+                        continue;
+                    }
                     const size_t smem = (size_t)a.nst * stage_bytes + 1024 + 24 * 8 + 64;
                     cudaEvent_t e0, e1;
                     CK(cudaEventCreate(&e0));
@@ -232,7 +203,7 @@ int main() {
                     float best = 1e9f;
                     for (int rep = 0; rep < 4; ++rep) {
                         CK(cudaEventRecord(e0));
-                        bulk_kernel<<<sms, threads, smem>>>(d, a, mode, sink);
+                        stream_kernel<<<sms, 32, smem>>>(tm, a, sink);
                         CK(cudaEventRecord(e1));
                         CK(cudaEventSynchronize(e1));
                         float ms;
@@ -240,9 +211,10 @@ int main() {
                         if (rep > 0 && ms < best) best = ms;
                     }
                     CK(cudaGetLastError());
-                    printf(",\n{\"mode\": \"bulk1d_per_column\", \"ncols\": %d, \"hold_clk_per_row\": %d, \"threads\": %d, \"rows_per_stage\": %d, \"stages\": %d, \"ms\": %.4f, \"gbs\": %.1f, \"hold_only_ms\": %.4f}",
-                           ncols, hold, threads, rows_stage, a.nst, best, 8.0 * a.rows_cta * sms * ncols / best / 1e6,
-                           hold * (double)a.rows_cta / 1.965e6);
+                    printf("%s{\"mode\": \"tensor2d\", \"box_rows\": %d, \"swizzle\": \"%s\", \"ncols\": %d, \"hold_clk_per_row\": %d, \"rows_per_stage\": %d, \"stages\": %d, \"ms\": %.4f, \"gbs\": %.1f, \"hold_only_ms\": %.4f}",
+                           first ? "" : ",\n", boxr, boxr == 16 ? "128B" : "none", ncols, hold, rows_stage, a.nst, best,
+                           8.0 * n * ncols / best / 1e6, hold * (double)a.rows_cta / 1.965e6);
+                    first = false;
                     fflush(stdout);
                 }
     for (int grid_mult : {1, 2, 4, 8}) {
