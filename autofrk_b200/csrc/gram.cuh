@@ -29,6 +29,9 @@ struct GramMidTile {
     unsigned char isz, warp, slot, pad;   // logical warp and accumulator slot that hold it
 };
 struct GramMidPlan {
+    // staged column blocks of a stage: F blocks then Z blocks; the last block of each matrix is trimmed to its valid
+    // 8-column groups.  blk_off: byte offset inside a stage, blk_cols: columns staged (box width), stage_bytes: total
+    int blk_off[8] = {0}, blk_cols[8] = {0}, stage_bytes = 0;
     GramMidUnit units[GRAM_MID_WARPS * GRAM_MID_UNITS];
     std::vector<GramMidTile> tiles;
     int nsets = 0, kb = 0, nblocks = 0, nunits = 0;
@@ -45,6 +48,7 @@ struct GramWorkspace {
     int last_nsplit = 0, last_npairs = 0;
     DevBuf<double> mid_tab;  // mid path: unit table + tile table of the cached shape
     int mid_K = -1, mid_T = -1, mid_ntiles = 0, mid_nsets = 0, mid_kb = 0, mid_nblocks = 0;
+    int mid_blk_off[8] = {0}, mid_blk_cols[8] = {0}, mid_stage_bytes = 0;
     bool mid_ok = false;
     const char* last_path = "";
     StreamGuard guard;       // orders calls that reuse this workspace from different streams

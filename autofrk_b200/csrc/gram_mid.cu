@@ -46,16 +46,18 @@ constexpr int MKR = 32;                    // rows per stage
 constexpr int MKQ = MKR / 4;               // k4-steps per stage
 constexpr int MPITCH = MBOXR * 8;                     // bytes between columns of a staged block: 36 doubles == 4 (mod 16)
 constexpr int MGROUP_BYTES = 8 * MPITCH;             // one 8-column group
-constexpr int MSLOT_BYTES = MCB * MPITCH;            // 9 KB: one column block of one stage = one TMA box
+constexpr int MSLOT_BYTES = MCB * MPITCH;            // 9 KB: a full 32-column block of one stage = one TMA box
 constexpr int MNW = GRAM_MID_WARPS;
 constexpr int MNT = MNW * 32;
 constexpr int MNU = GRAM_MID_UNITS;        // units per warp
 constexpr int MAXBLK = 8;
-constexpr int MAXST = 12;
+constexpr int MAXST = 16;
 constexpr size_t MID_SMEM_BUDGET = 222 * 1024;   // eight 27 KB stages (three column blocks) must fit
 
 struct MidArgs {
     int K, T, kb, nblocks, nst, nsets, ntiles;
+    int stage_bytes;              // sum of the staged blocks (the last block of F and of Z is trimmed to its 8-column groups)
+    int blk_off[MAXBLK], blk_col[MAXBLK], blk_map[MAXBLK];   // per block: byte offset in a stage, first column, tensor map
     int64_t n, rows_cta;
     const double* w;
     const GramMidUnit* units;     // [MNW][MNU] (device)
@@ -126,10 +128,11 @@ __device__ __forceinline__ void mid_unit_dispatch(int kind, uint32_t As, int lan
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(MNT, 1)
-gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmZ, const MidArgs a) {
+gram_mid_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3, const MidArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* const base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = a.nblocks * MSLOT_BYTES;
+    const int stage_bytes = a.stage_bytes;
     uint64_t* const full = reinterpret_cast<uint64_t*>(base + size_t(a.nst) * stage_bytes);
     uint32_t* const done = reinterpret_cast<uint32_t*>(full + MAXST);
     double* const zzw = reinterpret_cast<double*>(done + MAXST + (MAXST & 1));   // one partial per warp
@@ -178,15 +181,17 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
 
     // the box this lane copies when its warp arms a stage: lane -> column block (one 36-row x 32-column box each)
     const int my_blk = lane;
-    const bool my_isz = my_blk >= a.kb;
-    const CUtensorMap* const my_tm = my_isz ? &tmZ : &tmF;
-    const int my_col = (my_isz ? my_blk - a.kb : my_blk) * MCB;
+    const bool my_has = my_blk < a.nblocks;
+    const int my_map = my_has ? a.blk_map[my_blk] : 0;
+    const CUtensorMap* const my_tm = my_map == 0 ? &tm0 : (my_map == 1 ? &tm1 : (my_map == 2 ? &tm2 : &tm3));
+    const int my_col = my_has ? a.blk_col[my_blk] : 0;
+    const int my_off = my_has ? a.blk_off[my_blk] : 0;
     const uint32_t stage_tx = uint32_t(stage_bytes);
     auto issue = [&](int slot, int step) {   // one whole warp
         if (lane == 0) mbar_expect_tx(&full[slot], stage_tx);
         __syncwarp();
-        if (my_blk < a.nblocks)
-            mid_tma_load_2d(base + size_t(slot) * stage_bytes + my_blk * MSLOT_BYTES, my_tm,
+        if (my_has)
+            mid_tma_load_2d(base + size_t(slot) * stage_bytes + my_off, my_tm,
                             int(r_begin + int64_t(step) * MKR), my_col, &full[slot]);
     };
     if (warp == 0)
@@ -221,7 +226,7 @@ gram_mid_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__
                 for (int e = lane; e < nchunks; e += 32) {
                     const int c = e / (MKR / 2), rp = e % (MKR / 2);
                     const int blk = a.kb + c / MCB, cc = c % MCB;
-                    const double2 v = *reinterpret_cast<const double2*>(As + blk * MSLOT_BYTES + cc * MPITCH + rp * 16);
+                    const double2 v = *reinterpret_cast<const double2*>(As + a.blk_off[blk] + cc * MPITCH + rp * 16);
                     if (WEIGHTED) {
                         const int64_t r = r_begin + int64_t(step) * MKR + 2 * rp;
                         const double w0 = (r < r_end) ? __ldg(a.w + r) : 0.0, w1 = (r + 1 < r_end) ? __ldg(a.w + r + 1) : 0.0;
@@ -328,11 +333,11 @@ EncodeFn mid_encode_fn() {
     }();
     return fn;
 }
-CUtensorMap mid_make_map(const double* ptr, int64_t rows, int cols, int64_t ld) {
+CUtensorMap mid_make_map(const double* ptr, int64_t rows, int cols, int64_t ld, int box_cols) {
     CUtensorMap tm;
     cuuint64_t gdim[2] = {cuuint64_t(rows), cuuint64_t(cols)};
     cuuint64_t gstr[1] = {cuuint64_t(ld) * 8};
-    cuuint32_t box[2] = {MBOXR, MCB};
+    cuuint32_t box[2] = {MBOXR, cuuint32_t(box_cols)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = mid_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), gdim, gstr, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -351,14 +356,27 @@ bool gram_mid_plan(int K, int T, GramMidPlan& P) {
     const int kb = (K + MCB - 1) / MCB, zb = (T + MCB - 1) / MCB;
     if (kb + zb > MAXBLK) return false;
     // units: {first row group, first column group (in block blk of F | Z), kind}; tiles listed as (a, b) local indices
+    // stage layout: full 32-column blocks, the last block of F and of Z trimmed to its valid 8-column groups
+    {
+        int off = 0;
+        for (int b = 0; b < kb + zb; ++b) {
+            const bool isz = b >= kb;
+            const int c0 = (isz ? b - kb : b) * MCB, ncol = isz ? T : K;
+            const int w = std::min(MCB, (ncol - c0 + 7) / 8 * 8);
+            P.blk_off[b] = off;
+            P.blk_cols[b] = w;
+            off += w * MPITCH;
+        }
+        P.stage_bytes = off;
+    }
     struct U { GramMidUnit u; int cost; int ga0; bool isz; int gb0; };
     std::vector<U> units;
     auto add = [&](int ga0, bool isz, int gb0, int nr, int nc, int kind) {
         U x{};
         x.ga0 = ga0; x.isz = isz; x.gb0 = gb0;
         x.u.ga0 = ga0; x.u.gb0 = gb0; x.u.isz = isz ? 1 : 0;
-        x.u.a_base = (ga0 / 4) * MSLOT_BYTES + (ga0 % 4) * MGROUP_BYTES;
-        x.u.b_base = ((isz ? kb : 0) + gb0 / 4) * MSLOT_BYTES + (gb0 % 4) * MGROUP_BYTES;
+        x.u.a_base = P.blk_off[ga0 / 4] + (ga0 % 4) * MGROUP_BYTES;
+        x.u.b_base = P.blk_off[(isz ? kb : 0) + gb0 / 4] + (gb0 % 4) * MGROUP_BYTES;
         x.u.kind = kind ? kind : 1 + (nr - 1) * 4 + (nc - 1);
         x.cost = kind == GRAM_MID_TRI24 ? 7 : (kind == GRAM_MID_TRI22 ? 3 : nr * nc);
         units.push_back(x);
@@ -488,6 +506,8 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
             ws.mid_nsets = P.nsets;
             ws.mid_kb = P.kb;
             ws.mid_nblocks = P.nblocks;
+            ws.mid_stage_bytes = P.stage_bytes;
+            for (int b = 0; b < 8; ++b) { ws.mid_blk_off[b] = P.blk_off[b]; ws.mid_blk_cols[b] = P.blk_cols[b]; }
         }
     }
     if (!ws.mid_ok) return false;
@@ -507,7 +527,8 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     a.nblocks = ws.mid_nblocks;
     a.nsets = ws.mid_nsets;
     a.ntiles = ws.mid_ntiles;
-    const int stage_bytes = a.nblocks * MSLOT_BYTES;
+    const int stage_bytes = ws.mid_stage_bytes;
+    a.stage_bytes = stage_bytes;
     a.nst = int(std::min<size_t>(MAXST, MID_SMEM_BUDGET / stage_bytes));
     a.nst -= a.nst % a.nsets;   // a ring slot is always consumed by the same set: its warps see the slot's phases in order
     const size_t smem = size_t(a.nst) * stage_bytes + 1024 + MAXST * 8 + (MAXST + 1) * 4 + MNW * 8 + 64;
@@ -520,10 +541,26 @@ bool gram_stats_mid_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     a.partial = ws.partial.p;
     a.zzcta = ws.partial.p + size_t(grid) * MNW * MNU * 8 * 64;
 
-    const CUtensorMap tmF = mid_make_map(dF, n, K, ldf);
-    const CUtensorMap tmZ = (T > 0) ? mid_make_map(dZ, n, T, ldz) : tmF;
-    if (dw) gram_mid_kernel<true><<<grid, MNT, smem, st>>>(tmF, tmZ, a);
-    else gram_mid_kernel<false><<<grid, MNT, smem, st>>>(tmF, tmZ, a);
+    // tensor maps: full-width boxes of F / Z and, where the last block is narrower, a box of exactly its width
+    CUtensorMap maps[4];
+    int nmaps = 0, key[4] = {-1, -1, -1, -1};
+    auto map_for = [&](bool isz, int width) {
+        const int k = (isz ? 1000 : 0) + width;
+        for (int i = 0; i < nmaps; ++i)
+            if (key[i] == k) return i;
+        maps[nmaps] = isz ? mid_make_map(dZ, n, T, ldz, width) : mid_make_map(dF, n, K, ldf, width);
+        key[nmaps] = k;
+        return nmaps++;
+    };
+    for (int b = 0; b < a.nblocks; ++b) {
+        const bool isz = b >= a.kb;
+        a.blk_off[b] = ws.mid_blk_off[b];
+        a.blk_col[b] = (isz ? b - a.kb : b) * MCB;
+        a.blk_map[b] = map_for(isz, ws.mid_blk_cols[b]);
+    }
+    for (int i = nmaps; i < 4; ++i) maps[i] = maps[0];
+    if (dw) gram_mid_kernel<true><<<grid, MNT, smem, st>>>(maps[0], maps[1], maps[2], maps[3], a);
+    else gram_mid_kernel<false><<<grid, MNT, smem, st>>>(maps[0], maps[1], maps[2], maps[3], a);
     FRK_CUDA(cudaGetLastError());
     gram_mid_reduce_kernel<<<a.ntiles, 256, 0, st>>>(a, dtiles, grid, dpacked);
     FRK_CUDA(cudaGetLastError());
