@@ -6,6 +6,7 @@
 #include <thread>
 #include <vector>
 #include "capi_internal.cuh"
+#include "host_staging.cuh"
 
 namespace frk_capi {
 
@@ -86,15 +87,6 @@ frk_plan* make_plan(const double* Xu, int64_t n, int32_t d, const double* BBBH, 
 // pinned buffers owned by the plan at the PCIe rate while a few host threads scatter the previous chunk's columns into
 // the caller's matrix (measured: 25.7 GB/s with 4 threads, 31 GB/s with 8).  FRK_HOST_STAGING=0 turns it off;
 // FRK_HOST_COPY_THREADS sets the thread count.
-bool host_pointer_is_pinned(const void* p) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return attr.type == cudaMemoryTypeHost;
-}
-
 struct ScatterJob {   // columns of one staged chunk (rows x k, dense) -> out[r0 .. r0 + rows, :] with leading dimension ldo
     std::vector<std::thread> threads;
     void start(const double* stage, int64_t rows, int k, double* out, int64_t ldo, int nthreads) {
@@ -155,15 +147,9 @@ void predict_host(frk_plan* plan, const double* xnew, int64_t n2, double* out, i
         const char* e = std::getenv("FRK_HOST_STAGING");
         return e ? std::atoi(e) : 1;
     }();
-    static const int copy_threads = [] {   // default: the host cores divided among the visible GPUs (one process each), 2..8
-        if (const char* e = std::getenv("FRK_HOST_COPY_THREADS")) return std::max(1, std::atoi(e));
-        int ndev = 1;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 1; }
-        const int hw = int(std::thread::hardware_concurrency());
-        return std::max(2, std::min(8, hw / std::max(1, ndev)));
-    }();
+    const int copy_threads = frk::host_copy_threads();
     const bool staged = staging_env != 0 && sizeof(double) * size_t(n2) * size_t(k) >= (size_t(64) << 20) &&
-                        !host_pointer_is_pinned(out);
+                        !frk::host_pointer_is_pinned(out);
     if (staged && plan->hstage_doubles < size_t(rc) * k) {
         for (int b = 0; b < 2; ++b) {
             if (plan->hstage[b]) cudaFreeHost(plan->hstage[b]);

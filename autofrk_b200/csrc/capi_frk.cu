@@ -1,5 +1,6 @@
 // C ABI, part 2: fixed-rank-kriging reductions (K4, K5) and the fused predict -> reduce paths.
 #include "capi_internal.cuh"
+#include "host_staging.cuh"
 #include "panel_gemm.cuh"
 
 using frk_capi::guarded;
@@ -220,11 +221,8 @@ int32_t frk_gram_stats(const double* F, int64_t n, int32_t K, const double* Z, i
                 const int b = c & 1;
                 const int64_t rows = std::min(rc, n - r0);
                 if (c >= 2) FRK_CUDA(cudaStreamWaitEvent(s_copy, ev_done[b], 0));
-                FRK_CUDA(cudaMemcpy2DAsync(dF[b].p, sizeof(double) * rc, F + r0, sizeof(double) * n, sizeof(double) * rows,
-                                           size_t(K), cudaMemcpyHostToDevice, s_copy));
-                if (T > 0)
-                    FRK_CUDA(cudaMemcpy2DAsync(dZ[b].p, sizeof(double) * rc, Z + r0, sizeof(double) * n,
-                                               sizeof(double) * rows, size_t(T), cudaMemcpyHostToDevice, s_copy));
+                frk::upload_matrix(dF[b].p, rc, F + r0, n, rows, K, s_copy);     // pageable R matrices: through the pinned ring
+                if (T > 0) frk::upload_matrix(dZ[b].p, rc, Z + r0, n, rows, T, s_copy);
                 if (weights)
                     FRK_CUDA(cudaMemcpyAsync(dW[b].p, weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, s_copy));
                 FRK_CUDA(cudaEventRecord(ev_in[b], s_copy));

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <vector>
 #include "capi_internal.cuh"
+#include "host_staging.cuh"
 #include "panel_gemm.cuh"
 
 using frk_capi::guarded;
@@ -272,16 +273,15 @@ int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, co
         const int K = mp->k, d = mp->d;
         const int64_t ld = (n2 + 1) / 2 * 2;  // even leading dimension: every chunk stays 16-byte aligned
         frk::DevBuf<double> dx(size_t(ld) * d), dZ, dw, packed(frk::gram_packed_len(K, T));
-        FRK_CUDA(cudaMemcpy2D(dx.p, sizeof(double) * ld, xnew, sizeof(double) * n2, sizeof(double) * n2, size_t(d),
-                              cudaMemcpyHostToDevice));
+        cudaStream_t st = nullptr;   // this thread's default stream; large pageable inputs go up through the pinned ring
+        frk::upload_matrix(dx.p, ld, xnew, n2, n2, d, st);
         if (T > 0) {
             dZ.alloc(size_t(ld) * T);
-            FRK_CUDA(cudaMemcpy2D(dZ.p, sizeof(double) * ld, Z, sizeof(double) * n2, sizeof(double) * n2, size_t(T),
-                                  cudaMemcpyHostToDevice));
+            frk::upload_matrix(dZ.p, ld, Z, n2, n2, T, st);
         }
         if (weights) {
             dw.alloc(static_cast<size_t>(ld));
-            FRK_CUDA(cudaMemcpy(dw.p, weights, sizeof(double) * n2, cudaMemcpyHostToDevice));
+            frk::upload_matrix(dw.p, ld, weights, n2, n2, 1, st);
         }
         int32_t rc = frk_plan_predict_gram_dev(plan, dx.p, n2, ld, T > 0 ? dZ.p : nullptr, T, ld, weights ? dw.p : nullptr,
                                                packed.p, 0, nullptr);

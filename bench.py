@@ -460,6 +460,12 @@ def fused_e2e(plan, x_page, K, wall, world):
     t = wall(lambda: check(lib.frk_plan_predict_gram(plan._h, ptr(x_page), n2e, ptr(Z), 1, None, ptr(Gm), ptr(Cm), ptr(zz))), 2)
     out["predict_gram_T1"] = {"value": world * n2e * K / t, "unit": UNIT, "wall_ms": t * 1e3,
                               "h2d_bytes_per_step": int(n2e * (d + 1) * 8), "d2h_bytes_per_step": int((K * K + K + 1) * 8)}
+    Z = np.asfortranarray(rng.standard_normal((n2e, 100)))       # a 100-replicate fit: 3.2 GB of data go up per call
+    Cm = np.empty((K, 100), order="F")
+    t = wall(lambda: check(lib.frk_plan_predict_gram(plan._h, ptr(x_page), n2e, ptr(Z), 100, None, ptr(Gm), ptr(Cm), ptr(zz))), 2)
+    out["predict_gram_T100"] = {"value": world * n2e * K / t, "unit": UNIT, "wall_ms": t * 1e3,
+                                "h2d_bytes_per_step": int(n2e * (d + 100) * 8), "d2h_bytes_per_step": int((K * K + 100 * K + 1) * 8)}
+    del Z
     wv = np.asfortranarray(rng.standard_normal((K, 1)))
     R = rng.standard_normal((K, 3))
     V = np.asfortranarray(R @ R.T)

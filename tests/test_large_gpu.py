@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from util import TOL, colrel, within
+from util import TOL, colrel, relmax, within
 
 pytestmark = pytest.mark.gpu
 
@@ -258,3 +258,25 @@ def test_two_host_threads_and_two_streams():
     torch.cuda.synchronize()
     for k in range(6):
         assert torch.equal(outs[k], refs[k % 3]), k
+
+
+def test_large_pageable_inputs_go_through_the_pinned_ring():
+    """Host matrices above 64 MB reach the device through the two-slot pinned ring (host_staging.cu): whole-column
+    pieces, strided row chunks (frk_gram_stats streams F in row chunks), and columns longer than one 128 MB slot."""
+    from autofrk_b200 import frk as GF
+
+    rng = np.random.default_rng(31)
+    n, K, T = 1_200_000, 40, 12                      # F 384 MB (row-chunked, strided columns), Z 115 MB
+    F = np.asfortranarray(rng.standard_normal((n, K)))
+    Z = np.asfortranarray(rng.standard_normal((n, T)))
+    Gm, Cm, zz = GF.gram_stats(F, Z)
+    within("test_large_pageable_inputs:G", relmax(Gm, F.T @ F), 1e-12)
+    within("test_large_pageable_inputs:C", relmax(Cm, F.T @ Z), 1e-12)
+    assert abs(zz - np.sum(Z * Z)) < 1e-12 * zz
+    del F, Z
+    n = 17_000_000                                    # one column = 136 MB > a slot: split by rows
+    f = np.asfortranarray(rng.standard_normal((n, 2)))
+    z = np.asfortranarray(rng.standard_normal((n, 1)))
+    Gm, Cm, zz = GF.gram_stats(f, z)
+    within("test_large_pageable_inputs:G_long_columns", relmax(Gm, f.T @ f), 1e-12)
+    within("test_large_pageable_inputs:C_long_columns", relmax(Cm, f.T @ z), 1e-11)

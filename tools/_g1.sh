@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_frk_gpu.py tests/test_large_gpu.py -q -x -k "gram or two_host" > gpurun_out/r2_t13.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t13.log
-python tools/gram_probe.py > gpurun_out/r2_gram_probe.log 2>&1
-cp gpurun_out/gram_probe.json gpurun_out/gram_probe_r02_v10.json
-REPS=1 ncu --set full --import-source on --clock-control none -k regex:gram_mid_kernel -c 3 -f -o gpurun_out/gram_mid_r02_v10 python tools/gram_ncu.py 5000000,32,4 5000000,64,4 5000000,100,1 > gpurun_out/r2_ncu_mid.log 2>&1
-tail -4 gpurun_out/r2_t13.log; grep '"path": "mid"' gpurun_out/r2_gram_probe.log | cut -c1-130
+python -m pytest tests -q -m gpu > gpurun_out/r2_t14.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t14.log
+tail -4 gpurun_out/r2_t14.log
+python tools/e2e_probe.py 4000000 > gpurun_out/e2e3.log 2>&1; tail -2 gpurun_out/e2e3.log | cut -c1-1200
