@@ -403,10 +403,52 @@ bool gram_mid_plan(int K, int T, GramMidPlan& P) {
             for (int i = 0; i < na; i += 2) add(4 * ba + i, isz, g0, std::min(2, na - i), nc, 0);
         }
     }
-    const int nunits = int(units.size());
-    if (nunits > MNW * MNU) return false;
-    P.nsets = (nunits <= MNW * MNU / 4) ? 4 : (nunits <= MNW * MNU / 2 ? 2 : 1);
+    if (int(units.size()) > MNW * MNU) return false;
+    P.nsets = (int(units.size()) <= MNW * MNU / 4) ? 4 : (int(units.size()) <= MNW * MNU / 2 ? 2 : 1);
+    {
+        static const int max_sets = [] {
+            const char* e = std::getenv("FRK_GRAM_MID_MAXSETS");   // tuning aid
+            return e ? std::atoi(e) : 4;
+        }();
+        while (P.nsets > max_sets && P.nsets > 1) P.nsets /= 2;
+    }
     const int wps = MNW / P.nsets;
+    // Warps of a set finish a stage together only if they carry similar work: while slots are free, the heaviest
+    // two-row unit above the per-warp mean is split into its two rows (a 2 x nc rectangle into two 1 x nc ones; the
+    // triangles of a diagonal block into their rows).  Costs one more fragment load per DMMA in the split units.
+    {
+        static const int split_env = [] {
+            const char* e = std::getenv("FRK_GRAM_MID_SPLIT");   // tuning aid: threshold in percent of the mean; 0 = never split
+            return e ? std::atoi(e) : 115;
+        }();
+        int total = 0;
+        for (const U& x : units) total += x.cost;
+        const double mean = double(total) / wps;
+        const int split_pct = (P.nsets == 1) ? std::max(split_env, 160) : split_env;   // one set: all 16 warps share every stage anyway
+        while (split_env && int(units.size()) < wps * MNU) {
+            int h = -1;
+            for (int i = 0; i < int(units.size()); ++i) {
+                const int kind = units[i].u.kind;
+                const bool two_rows = kind == GRAM_MID_TRI24 || kind == GRAM_MID_TRI22 || (kind >= 5 && kind <= 8);
+                if (two_rows && units[i].cost * 100.0 > split_pct * mean && (h < 0 || units[i].cost > units[h].cost)) h = i;
+            }
+            if (h < 0) break;
+            const U x = units[h];
+            units.erase(units.begin() + h);
+            if (x.u.kind == GRAM_MID_TRI24) {
+                add(x.ga0, false, x.gb0, 1, 4, 0);
+                add(x.ga0 + 1, false, x.gb0 + 1, 1, 3, 0);
+            } else if (x.u.kind == GRAM_MID_TRI22) {
+                add(x.ga0, false, x.gb0, 1, 2, 0);
+                add(x.ga0 + 1, false, x.gb0 + 1, 1, 1, 0);
+            } else {
+                const int nc = (x.u.kind - 1) % 4 + 1;
+                add(x.ga0, x.isz, x.gb0, 1, nc, 0);
+                add(x.ga0 + 1, x.isz, x.gb0, 1, nc, 0);
+            }
+        }
+    }
+    const int nunits = int(units.size());
     // bins whose loads must be equal: with s sets a logical sub-partition p shares the pipe with p + k*4/s
     const int nbins = 4 / P.nsets;
     std::stable_sort(units.begin(), units.end(), [](const U& x, const U& y) { return x.cost > y.cost; });

@@ -37,6 +37,11 @@ def run(n, K, T, reps=3, path=""):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "small":      # only the shapes of the register-resident kernel (A/B of its tuning aids)
+        out = [run(5_000_000, K, T, reps=5, path="mid")
+               for K, T in ((24, 1), (32, 4), (48, 8), (64, 4), (64, 1), (80, 1), (100, 1), (128, 4), (128, 16), (100, 20))]
+        json.dump(out, open("gpurun_out/gram_probe_small.json", "w"), indent=1)
+        sys.exit(0)
     out = [run(5_000_000, 500, 100), run(2_000_000, 500, 1), run(1_000_000, 1000, 100),
            run(5_000_000, 200, 20), run(5_000_000, 256, 1), run(2_000_000, 446, 1)]
     # shapes default autoFRK() selects (K = 18 ... ~130): the register-resident kernel against the ones it replaces
