@@ -24,10 +24,9 @@ NVCC_FLAGS = [
     # stream 0 in this library = the calling host thread's own default stream: the K x K stages (launches without a
     # stream argument, blocking copies) of two host threads do not serialise on the legacy null stream
     "--default-stream", "per-thread",
-    # stream 0 in this library = the calling host thread's own default stream: the K x K stages (launches without a
-    # stream argument, blocking copies) of two host threads do not serialise on the legacy null stream
-    "--default-stream", "per-thread",
     "-Xcompiler", "-fPIC",
+    # tuning aid: extra flags for an experimental build, e.g. FRK_NVCC_EXTRA="-DFRK_EXPERIMENTAL_CONFIGS" 
+    *os.environ.get("FRK_NVCC_EXTRA", "").split(),
 ]
 LINK_LIBS = ["-lcusolver", "-lcublas"]
 

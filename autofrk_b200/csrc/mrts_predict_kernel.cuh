@@ -550,10 +550,10 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     predict_info<PredictCfg<D, 8, 2, 4, 1, 16, 4>>(),  /* BM 256, BN  16 */                                \
     predict_info<PredictCfg<D, 4, 4, 4, 1, 32, 4>>(),  /* BM 128, BN  32, 8 Phi/thread */                  \
     predict_info<PredictCfg<D, 4, 4, 4, 2, 32, 4>>(),  /* BM 128, BN  64 */                                \
-    predict_info<PredictCfg<D, 4, 4, 4, 3, 16, 4>>(),  /* BM 128, BN  96 */                                \
-    predict_info<PredictCfg<D, 4, 4, 4, 4, 16, 4>>(),  /* BM 128, BN 128 */                                \
+    predict_info<PredictCfg<D, 4, 4, 4, 3, 16, 4, 2, false, true>>(), /* BM 128, BN  96, knots in smem */   \
+    predict_info<PredictCfg<D, 4, 4, 4, 4, 16, 4, 2, false, true>>(), /* BM 128, BN 128, knots in smem */   \
     predict_info<PredictCfg<D, 2, 8, 4, 3, 16, 4>>(),  /* BM  64, BN 192, 2 Phi/thread */                  \
-    predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>(),  /* BM  96, BN 200, 4 Phi/thread, 15 warps */        \
+    predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 3, 3, false, true>>(), /* BM 96, BN 200, 4 Phi/thread, 15 warps, Phi 3 ahead, knots in smem */ \
     predict_info<PredictCfg<D, 2, 8, 4, 4, 16, 4, 2, false, true>>(), /* BM  64, BN 256, knots in smem */   \
     predict_info<PredictCfg<D, 2, 8, 4, 5, 16, 3, 3, false, true>>(), /* BM 64, BN 320, Phi 3 ahead, knots in smem */ \
     predict_info<PredictCfg<D, 1, 16, 4, 3, 16, 3, 3, true>>(), /* BM 32, BN 384, 1 Phi/thread, Phi 3 ahead, split Phi */ \
@@ -568,7 +568,10 @@ const PredictKernelInfo* predict_kernels_d3(int* count);
     , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 3, 2>>() /* 16: BN 512, 3 stages, AHEAD 2 (v6) */         \
     , predict_info<PredictCfg<D, 1, 16, 4, 4, 16, 2, 3, true>>() /* 17: BN 512 with split Phi */            \
     , predict_info<PredictCfg<D, 1, 8, 4, 8, 16, 3>>()     /* 18: BN 512, 8 fat warps (32 x 64 tiles) */     \
-    , predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()     /* 19: BN 200, 20 thin warps, 2 Phi/thread */
+    , predict_info<PredictCfg<D, 4, 5, 2, 5, 20, 4>>()     /* 19: BN 200, 20 thin warps, 2 Phi/thread */   \
+    , predict_info<PredictCfg<D, 3, 5, 4, 5, 20, 4>>()     /* 20: BN 200, 4 stages, Phi 2 ahead, knots from global memory (r01) */ \
+    , predict_info<PredictCfg<D, 4, 4, 4, 4, 16, 4>>()     /* 21: BN 128, knots from global memory (r01) */ \
+    , predict_info<PredictCfg<D, 4, 4, 4, 3, 16, 4>>()     /* 22: BN 96, knots from global memory (r01) */
 #else
 #define FRK_PREDICT_EXTRA_CONFIGS(D)
 #endif
