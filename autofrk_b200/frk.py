@@ -8,9 +8,9 @@ device (K4 Gram reductions, K1 basis evaluation) and every K x K eigen-stage in 
   selectBasis       R/autoFRK.R:199-331          indeMLE              R/autoFRK.R:739-843
   autoFRK           R/autoFRK.R:121-197          predict_FRK          R/autoFRK.R:1168-1423
 The LatticeKrig fine-scale branch (cMLElk, SURVEY.md section 2 #20: out of scope) raises NotImplementedError.  Data with
-NAs run through the masked statistics + EM0miss / kNN imputation entry points built in round 1; the
-one thing such a model cannot do here is `predict_FRK(se_report=True)` -- the per-replicate standard errors of
-R/autoFRK.R:1224-1245 are not implemented and raise NotImplementedError rather than returning a wrong se.
+NAs run through the masked statistics + EM0miss / kNN imputation entry points built in round 1;
+for such a model `predict_FRK(se_report=True)` returns the per-replicate standard errors of R/autoFRK.R:1224-1245,
+computed from per-replicate masked Grams (_missing_se_covariances).
 Nothing falls back to host arithmetic.
 """
 from __future__ import annotations
@@ -459,6 +459,86 @@ def autoFRK(Data, loc, mu=0.0, D=None, G=None, finescale=False, maxit=50, tolera
     return obj
 
 
+def _missing_se_covariances(obj):
+    """R/autoFRK.R:1225-1242: a model fitted through EM0miss gets one V per replicate,
+    V_t = M - t(G_t M) invCz(s De_t, L_t, G_t M) over the rows observed in replicate t (pinfo$pick, pinfo$D).
+    With R = s De_t diagonal this is K x K algebra on t(G_t) R^-1 G_t: the per-replicate NA-masked weighted Grams
+    come from ONE pass over the rows of the basis (frk_masked_stats), each V_t from frk_krige_from_stats."""
+    G = obj["G"]
+    pinfo = obj.get("pinfo") or {}
+    Gall = G.X if isinstance(G, MrtsBasis) else fmat(G, "G")
+    pick = np.asarray(pinfo.get("pick", np.arange(Gall.shape[0])))
+    D0 = np.ones(Gall.shape[0]) if "D" not in pinfo else np.asarray(pinfo["D"], dtype=np.float64)
+    D0 = np.ascontiguousarray(D0[pick])                                          # D0 <- pinfo$D[pick, pick]  :1227
+    miss = np.asarray(obj["missing"]["miss"]) == 1                               # :1228
+    Fk = np.asfortranarray(Gall[pick])                                           # Fk <- object$G[pick, ]     :1229
+    M = fmat(obj["M"], "M")
+    K = M.shape[0]
+    TT = fmat(obj["w"], "w").shape[1]
+    if miss.shape[1] < TT:
+        # empty replicates were dropped before EM0miss (:746-750) but object$w keeps their columns (:834-836):
+        # miss[, tt] fails in R for the trailing replicates
+        raise IndexError("subscript out of bounds (the model was fitted with empty replicates: R/autoFRK.R:1233)")
+    if miss.shape[0] != Fk.shape[0] or Fk.shape[1] != K:
+        raise ValueError("Dimensions of the missing-data pattern, object$G and object$M are not compatible!")
+    s = float(obj["s"])
+    if not s > 0:
+        raise ValueError("object$s * De is singular (s = 0): solve() fails in invCz (R/autoFRK.R:847)")
+    O = np.asfortranarray(~miss[:, :TT], dtype=np.uint8)
+    Z0 = np.zeros((Fk.shape[0], TT), order="F")
+    G_all = np.empty((K, K, TT), order="F")
+    c_all = np.empty((K, TT), order="F")
+    zz_all = np.empty(TT)
+    nobs = np.empty(TT, dtype=np.int64)
+    check(lib.frk_masked_stats(ptr(Z0), O.ctypes.data_as(C.c_void_p), ptr(Fk), ptr(D0), Fk.shape[0], K, TT, ptr(G_all),
+                               ptr(c_all), ptr(zz_all), nobs.ctypes.data_as(C.c_void_p)))
+    Vs = []
+    c0 = np.zeros((K, 1), order="F")
+    coef = np.empty((K, 1), order="F")
+    for tt in range(TT):                                                         # :1232-1241
+        Gg = np.asfortranarray(G_all[:, :, tt] / s)                              # t(G) solve(s De) G
+        V = np.empty((K, K), order="F")
+        check(lib.frk_krige_from_stats(ptr(Gg), ptr(c0), 1, ptr(M), K, 1, ptr(coef), ptr(V)))
+        Vs.append(V)
+    return Vs
+
+
+def _predict_with_missing_se(obj, newloc, basis, mu_new):
+    """predict.FRK(se.report = TRUE) for a model with a "missing" attribute (R/autoFRK.R:1216, 1224-1245):
+    yhat = basis %*% w as always, se[, t] from the replicate's own V_t.  One fused pass per replicate
+    (columns [w_t | factor of V_t] behind the basis evaluation) when the basis is evaluated here."""
+    G = obj["G"]
+    w = fmat(obj["w"], "w")
+    K, TT = w.shape
+    Vs = _missing_se_covariances(obj)
+    fused = basis is None and newloc is not None
+    if fused:
+        x = fmat(newloc, "newloc")
+        if G.X.shape[1] != K:
+            raise ValueError("Dimensions of basis and object$w are not compatible!")
+        if G.X.shape[1] - G.Xu.shape[1] - 1 <= 0:
+            basis, fused = predict_mrts(G, x), False                              # polynomial-only basis (k* = 0)
+    if not fused:
+        B = fmat(G.X if isinstance(G, MrtsBasis) else G, "G") if basis is None else fmat(basis, "basis")
+        if newloc is not None and B.shape[0] != fmat(newloc).shape[0]:
+            raise ValueError("Dimensions of newloc and basis are not compatible!")
+        if B.shape[1] != K:
+            raise ValueError("Dimensions of basis and object$w are not compatible!")
+    n2 = x.shape[0] if fused else B.shape[0]
+    yhat = np.empty((n2, TT), order="F")
+    se = np.empty((n2, TT), order="F")
+    yt, st = np.empty((n2, 1), order="F"), np.empty(n2)
+    for tt in range(TT):
+        wt = np.asfortranarray(w[:, tt:tt + 1])
+        if fused:
+            check(lib.frk_plan_predict_frk(G.plan()._h, ptr(x), n2, ptr(wt), 1, ptr(Vs[tt]), ptr(yt), ptr(st)))
+        else:
+            check(lib.frk_basis_predict_frk(ptr(B), n2, K, ptr(wt), 1, ptr(Vs[tt]), ptr(yt), ptr(st)))
+        yhat[:, tt] = yt[:, 0]
+        se[:, tt] = st
+    return {"pred.value": yhat + mu_new, "se": se}
+
+
 def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=None, mu_new=0.0, se_report=False):
     """R/autoFRK.R:1168-1423, LKobj = NULL and obsData = NULL: yhat = basis %*% w (:1216),
     se = sqrt(pmax(0, rowSums((basis %*% V) * basis))) (:1220), both fused behind the basis evaluation."""
@@ -478,10 +558,7 @@ def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=N
     w = fmat(obj["w"], "w")
     K, TT = w.shape
     if se_report and obsData is None and obj.get("missing") is not None:
-        # R/autoFRK.R:1224-1245: a model fitted through EM0miss gets one V per replicate (rows observed in that
-        # replicate, pinfo$pick / D, invCz); object$V is NOT the right covariance there
-        raise NotImplementedError("predict_FRK(se_report=True) for a model fitted with missing data (per-replicate "
-                                  "standard errors, R/autoFRK.R:1224-1245) is not implemented")
+        return _predict_with_missing_se(obj, newloc, basis, mu_new)               # :1224-1245
     V = fmat(obj["V"], "V") if se_report else None
     if V is not None and V.shape != (K, K):
         raise ValueError("Dimensions of object$V and object$w are not compatible!")

@@ -451,23 +451,38 @@ def selectBasis(Data, loc, maxK=None, Kseq=None, maxknot=5000, Fk=None, n_neighb
     return out
 
 
-def indeMLE(Data, Fk, wSave=False, sigma=0.0):
-    """R/autoFRK.R:739-843, isimat & no-NA branch (:778-803)."""
+def indeMLE(Data, Fk, wSave=False, sigma=0.0, Ddiag=None, maxit=50, avgtol=1e-6):
+    """R/autoFRK.R:739-843: isimat & no-NA branch (:778-803); with NAs (diagonal D) the EM0miss branch (:829-841)
+    after dropping empty replicates (:746-750) and never-observed rows (:754-771)."""
     Data = _as2d(Data)
+    Fk = np.asarray(Fk, dtype=np.float64)
     if np.isnan(Data).any():
-        raise NotImplementedError("EM0miss path (missing data) is out of scope")
-    out = cMLEimat(np.asarray(Fk), Data, s=sigma, wSave=wSave)  # :787
+        TT, K = Data.shape[1], Fk.shape[1]
+        notempty = np.nonzero((~np.isnan(Data)).sum(axis=0) > 0)[0]            # :746-747
+        Data = Data[:, notempty]                                               # :749
+        keep = (~np.isnan(Data)).sum(axis=1) > 0                               # del <- which(rowSums(...) == 0)  :754
+        pick = np.nonzero(keep)[0]                                             # :755, :762
+        D0 = np.ones(Fk.shape[0]) if Ddiag is None else np.asarray(Ddiag, dtype=np.float64).ravel()   # :759
+        out = EM0miss(Fk[keep], Data[keep], D0[keep], maxit, avgtol, wSave)     # :830
+        if wSave:
+            w = np.zeros((K, TT))                                              # :834-836
+            w[:, notempty] = out["w"]
+            out["w"] = w
+            out["pinfo"] = {"D": D0, "pick": pick}                             # :838
+            out["missing"] = {"miss": np.isnan(Data[keep]).astype(float), "maxit": maxit, "avgtol": avgtol}  # :731-734
+        return out
+    out = cMLEimat(Fk, Data, s=sigma, wSave=wSave)             # :787
     if "v" in out:
         out["s"] = out["v"] if sigma == 0 else sigma           # :788-795
         del out["v"]
     return out
 
 
-def autoFRK(Data, loc, mu=0.0, G=None, maxK=None, Kseq=None, maxknot=5000):
-    """R/autoFRK.R:121-197, finescale=FALSE, method='fast', D = I, no NA."""
+def autoFRK(Data, loc, mu=0.0, G=None, maxK=None, Kseq=None, maxknot=5000, method="fast"):
+    """R/autoFRK.R:121-197, finescale=FALSE, D = I; method = "EM" needs G (selectBasis with NAs is not restated)."""
     Data = _as2d(Data) - mu                                    # :125
     Fk = G if G is not None else selectBasis(Data, loc, maxK=maxK, Kseq=Kseq, maxknot=maxknot)  # :126-133
-    if np.isnan(Data).any():
+    if method == "fast" and np.isnan(Data).any():
         Data = knn_impute(Data, loc)                           # :135-148 (method = "fast")
     F = Fk.X if isinstance(Fk, MrtsObject) else np.asarray(Fk)
     obj = indeMLE(Data, F, wSave=True)                         # :151
@@ -478,7 +493,7 @@ def autoFRK(Data, loc, mu=0.0, G=None, maxK=None, Kseq=None, maxknot=5000):
 
 def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=None, mu_new=0.0,
                 se_report=False):
-    """R/autoFRK.R:1168-1423, LKobj = NULL, no missing-data attribute."""
+    """R/autoFRK.R:1168-1423, LKobj = NULL (with or without the "missing" attribute of an EM0miss fit)."""
     if "w" not in obj:
         raise ValueError('input model (object) should use the option "wsave=TRUE"!')
     if newloc is None:
@@ -508,8 +523,25 @@ def predict_FRK(obj, obsData=None, obsloc=None, mu_obs=0.0, newloc=None, basis=N
         yhat = basis @ obj["w"]                                # :1216
         if se_report:
             TT = obj["w"].shape[1]
-            se = np.sqrt(np.maximum(0.0, np.sum((basis @ obj["V"]) * basis, axis=1)))  # :1220
-            se = np.repeat(se[:, None], TT, axis=1)            # :1222
+            if obj.get("missing") is None:
+                se = np.sqrt(np.maximum(0.0, np.sum((basis @ obj["V"]) * basis, axis=1)))  # :1220
+                se = np.repeat(se[:, None], TT, axis=1)        # :1222
+            else:                                              # :1224-1245, literal
+                se = np.full((basis.shape[0], TT), np.nan)
+                pick = obj["pinfo"]["pick"]                    # :1226
+                D0 = np.asarray(obj["pinfo"]["D"], dtype=np.float64)[pick]   # :1227 (diagonal)
+                miss = np.asarray(obj["missing"]["miss"]) == 1  # :1228
+                Fk = Gmat[pick, :]                             # :1229
+                M = obj["M"]
+                lam, U = sla.eigh(M)
+                lam, U = lam[::-1], U[:, ::-1]                 # dec <- eigen(M)  :1231
+                for tt in range(TT):                           # :1232 (miss[, tt] past its last column: R error)
+                    o = ~miss[:, tt]
+                    Gt = Fk[o, :]                              # :1233
+                    GM = Gt @ M                                # :1234
+                    L = Gt @ U @ np.diag(np.sqrt(np.maximum(lam, 0.0)))   # :1236-1239
+                    V = M - GM.T @ invCz(obj["s"] * D0[o], L, GM)          # :1240
+                    se[:, tt] = np.sqrt(np.maximum(0.0, np.sum((basis @ V) * basis, axis=1)))   # :1241-1242
     if obsData is not None:                                    # :1248-1274
         pick = np.nonzero(~np.isnan(obsData.ravel()))[0]
         if obsloc is None:

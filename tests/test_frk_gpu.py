@@ -554,7 +554,7 @@ def test_cMLEimat_scale_equivariance():
 
 def test_predict_FRK_argument_contract():
     """Corners of predict.FRK the reference treats specially (R/autoFRK.R:1214-1245): a model fitted with missing data has
-    per-replicate standard errors (not implemented here: loud, never a wrong se); obsloc without obsData leaves yhat
+    per-replicate standard errors (empty replicates dropped by the fit make R fail on miss[, tt]); obsloc without obsData leaves yhat
     undefined in R; w / V that do not match the basis are rejected before the device reads them."""
     from autofrk_b200 import frk as G, mrts as GM
 
@@ -580,5 +580,60 @@ def test_predict_FRK_argument_contract():
     miss = dict(obj)
     miss["missing"] = {"miss": np.zeros((n, 1))}
     assert G.predict_FRK(miss, newloc=newloc)["pred.value"].shape == (50, 1)       # yhat is the same formula (:1216)
-    with pytest.raises(NotImplementedError, match="per-replicate"):
-        G.predict_FRK(miss, newloc=newloc, se_report=True)
+    pm = G.predict_FRK(miss, newloc=newloc, se_report=True)                        # per-replicate V (:1224-1245)
+    assert pm["se"].shape == (50, 1) and np.all(np.isfinite(pm["se"])) and np.all(pm["se"] >= 0)
+    short = dict(obj)
+    short["w"] = np.hstack([obj["w"], np.zeros((K, 1))])                          # a dropped empty replicate keeps its column in w
+    short["missing"] = {"miss": np.zeros((n, 1))}
+    with pytest.raises(IndexError, match="subscript out of bounds"):
+        G.predict_FRK(short, newloc=newloc, se_report=True)
+
+
+def test_predict_FRK_per_replicate_se_after_EM_fit():
+    """predict.FRK(se.report = TRUE) on a model fitted through EM0miss (R/autoFRK.R:1224-1245): one V_t per replicate
+    from the rows observed in that replicate, pinfo$pick and pinfo$D; literal restatement in the oracle."""
+    import oracle as O
+    from autofrk_b200 import frk as G, mrts as GM
+
+    rng = np.random.default_rng(12)
+    n, T, K = 1400, 5, 12
+    loc = rng.random((n, 2))
+    Fo = O.mrts(loc[:150], K, loc)
+    Fg = GM.MrtsBasis(Fo.X, Fo.UZ, Fo.Xu, Fo.nconst, Fo.BBBH)
+    Z = Fo.X[:, 3:6] @ (rng.standard_normal((3, T)) * 4.0) + rng.standard_normal((n, T))
+    Z[rng.random(Z.shape) < 0.35] = np.nan
+    Z[5:40, :] = np.nan                                        # never-observed rows are dropped from the fit (pick)
+    ref = O.autoFRK(Z, loc, G=Fo, method="EM")
+    kept = int((~np.all(np.isnan(Z), axis=1)).sum())
+    assert kept <= n - 35 and ref["missing"]["miss"].shape == (kept, T) and ref["pinfo"]["pick"].size == kept
+    got = G.autoFRK(Z, loc, G=Fg, method="EM")
+    assert np.array_equal(got["pinfo"]["pick"], ref["pinfo"]["pick"])
+    assert np.array_equal(np.asarray(got["missing"]["miss"]) == 1, ref["missing"]["miss"] == 1)
+    within("test_predict_FRK_per_replicate_se_after_EM_fit:got[M]", relmax(got["M"], ref["M"]), 1e-13)   # observed 6.3e-16 on B200
+    newloc = rng.random((700, 2))
+    # the same fitted quantities on both sides: isolates predict.FRK
+    same = dict(ref)
+    same["G"] = Fg
+    pr = O.predict_FRK(ref, newloc=newloc, se_report=True)
+    assert pr["se"].shape == (700, T) and np.ptp(pr["se"], axis=1).max() > 0     # the columns really differ
+    for kind, pg in (("fused", G.predict_FRK(same, newloc=newloc, se_report=True)),
+                     ("basis", G.predict_FRK(same, newloc=newloc, basis=O.predict_mrts(Fo, newloc), se_report=True))):
+        within(f"test_predict_FRK_per_replicate_se_after_EM_fit:{kind}[pred.value]",
+               relmax(pg["pred.value"], pr["pred.value"]), 1e-13)   # observed 1.4e-15 on B200
+        # V_t = M - (...) cancels on both sides (SURVEY 8c (3)), as in test_predict_FRK_with_new_observations
+        within(f"test_predict_FRK_per_replicate_se_after_EM_fit:{kind}[se]", relmax(pg["se"], pr["se"]), 5e-6)   # observed 3.7e-07 on B200
+    # newloc = NULL: basis = object$G (all rows, observed or not)
+    pr0, pg0 = O.predict_FRK(ref, se_report=True), G.predict_FRK(same, se_report=True)
+    assert pg0["se"].shape == (n, T)
+    within("test_predict_FRK_per_replicate_se_after_EM_fit:default[se]", relmax(pg0["se"], pr0["se"]), 5e-6)   # observed 4.0e-07 on B200
+    # and end to end on the product's own fit
+    pe = G.predict_FRK(got, newloc=newloc, se_report=True)
+    within("test_predict_FRK_per_replicate_se_after_EM_fit:own_fit[se]", relmax(pe["se"], pr["se"]), 5e-6)   # observed 4.3e-07 on B200
+    # a non-identity diagonal D enters through pinfo$D
+    D = rng.random(n) + 0.5
+    refD = O.indeMLE(Z, Fo.X, wSave=True, Ddiag=D)
+    refD["G"] = Fo
+    sameD = dict(refD)
+    sameD["G"] = Fg
+    prD, pgD = O.predict_FRK(refD, newloc=newloc, se_report=True), G.predict_FRK(sameD, newloc=newloc, se_report=True)
+    within("test_predict_FRK_per_replicate_se_after_EM_fit:D[se]", relmax(pgD["se"], prD["se"]), 2e-6)   # observed 1.0e-07 on B200

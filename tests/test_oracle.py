@@ -257,3 +257,39 @@ def test_rigid_motion_invariance_of_the_eigen_columns(d):
         s = np.sign(np.sum(A * B, axis=0))
         err = np.max(np.max(np.abs(A * s - B), axis=0) / np.max(np.abs(B), axis=0))
         assert err < 1e-8, err          # eigenvector conditioning (relative gaps ~1e-3) times 1e-13-class perturbations
+
+
+def test_missing_data_predict_se_against_dense_algebra():
+    """The oracle's literal restatement of predict.FRK's per-replicate V (R/autoFRK.R:1224-1245, through invCz's
+    Woodbury form) against the dense definition V_t = M - M G_t' (s De_t + G_t M+ G_t')^-1 G_t M at a small size."""
+    rng = np.random.default_rng(3)
+    n, T, K = 160, 3, 7
+    loc = rng.random((n, 2))
+    Fo = O.mrts(loc[:40], K, loc)
+    Z = Fo.X[:, 3:5] @ rng.standard_normal((2, T)) * 3.0 + rng.standard_normal((n, T))
+    Z[rng.random(Z.shape) < 0.3] = np.nan
+    Z[:4] = np.nan
+    Z = np.hstack([Z, np.full((n, 1), np.nan)])                     # an empty replicate: dropped by the fit, kept in w
+    D = rng.random(n) + 0.5
+    obj = O.indeMLE(Z, Fo.X, wSave=True, Ddiag=D)
+    obj["G"] = Fo
+    assert obj["w"].shape == (K, T + 1) and np.all(obj["w"][:, T] == 0.0)
+    assert obj["pinfo"]["pick"].size == obj["missing"]["miss"].shape[0] <= n - 4
+    with pytest.raises(IndexError):                                  # miss[, tt] past the last kept replicate: R fails too
+        O.predict_FRK(obj, newloc=loc[:5], se_report=True)
+    obj["w"] = obj["w"][:, :T]
+    newloc = rng.random((30, 2))
+    out = O.predict_FRK(obj, newloc=newloc, se_report=True)
+    B = O.predict_mrts(Fo, newloc)
+    M, s = obj["M"], obj["s"]
+    lam, U = np.linalg.eigh(M)
+    Mp = (U * np.maximum(lam, 0.0)) @ U.T
+    pick = obj["pinfo"]["pick"]
+    for tt in range(T):
+        o = ~(obj["missing"]["miss"][:, tt] == 1)
+        Gt = Fo.X[pick][o]
+        Cm = np.diag(s * D[pick][o]) + Gt @ Mp @ Gt.T
+        V = M - M @ Gt.T @ np.linalg.solve(Cm, Gt @ M)
+        se = np.sqrt(np.maximum(0.0, np.sum((B @ V) * B, axis=1)))
+        assert np.max(np.abs(out["se"][:, tt] - se)) <= 1e-8 * np.max(se)
+    assert np.allclose(out["pred.value"], B @ obj["w"], rtol=0, atol=1e-12)
