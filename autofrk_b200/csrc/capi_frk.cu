@@ -1,4 +1,6 @@
 // C ABI, part 2: fixed-rank-kriging reductions (K4, K5) and the fused predict -> reduce paths.
+#include <functional>
+
 #include "capi_internal.cuh"
 #include "host_staging.cuh"
 #include "panel_gemm.cuh"
@@ -116,8 +118,12 @@ int64_t default_chunk_rows(const frk::MrtsPlan* mp, int K) {
     return std::max<int64_t>(wave, rc / wave * wave);
 }
 
+// `before_gram(r0, rows)` (optional) runs on the host between the launch of K1 and of K4 for each row chunk: the
+// host-buffer entry point uses it to bring that chunk's rows of Z up while K1 of the same chunk is running.
+using BeforeGram = std::function<void(int64_t, int64_t)>;
 void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, const double* dZ, int T, int64_t ldz,
-                  const double* dw, double* dpacked, int64_t chunk_rows, cudaStream_t st) {
+                  const double* dw, double* dpacked, int64_t chunk_rows, cudaStream_t st,
+                  const BeforeGram* before_gram = nullptr) {
     frk::MrtsPlan* mp = plan->mp;
     const int K = mp->k;
     if (chunk_rows <= 0) chunk_rows = default_chunk_rows(mp, K);
@@ -132,6 +138,7 @@ void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, con
     for (int64_t r0 = 0; r0 < n2; r0 += chunk_rows) {
         const int64_t rows = std::min(chunk_rows, n2 - r0);
         frk::plan_predict_basis_dev(mp, dx + r0, rows, ldx, plan->fchunk.p, chunk_rows, st);
+        if (before_gram) (*before_gram)(r0, rows);
         frk::gram_stats_dev(plan->fchunk.p, rows, K, chunk_rows, T > 0 ? dZ + r0 : nullptr, T, ldz, dw ? dw + r0 : nullptr,
                             plan->packed_tmp.p, ws, st);
         axpy_kernel<<<unsigned((plen + 255) / 256), 256, 0, st>>>(dpacked, plan->packed_tmp.p, int64_t(plen), first);
@@ -142,6 +149,39 @@ void predict_gram(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, con
 }
 
 }  // namespace
+
+namespace frk_capi {
+
+// predict -> Gram with Z still in HOST memory: the rows of Z that a chunk needs go up on a copy stream (through the
+// pinned ring when Z is pageable) while K1 evaluates that chunk's basis, and K4 of chunk i runs while the host stages
+// chunk i + 1 -- the upload of an n2 x T matrix (3.3 GB at 4 M rows, T = 100) leaves the critical path.
+void predict_gram_host_z(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, const double* hZ, int64_t ldzh,
+                         double* dZ, int T, int64_t ldz, const double* dw, double* dpacked, cudaStream_t st) {
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev = nullptr;
+    FRK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    FRK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    auto cleanup = [&] {
+        cudaStreamSynchronize(cs);
+        cudaEventDestroy(ev);
+        cudaStreamDestroy(cs);
+    };
+    const BeforeGram up = [&](int64_t r0, int64_t rows) {
+        frk::upload_matrix(dZ + r0, ldz, hZ + r0, ldzh, rows, T, cs);
+        FRK_CUDA(cudaEventRecord(ev, cs));
+        FRK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    };
+    try {
+        predict_gram(plan, dx, n2, ldx, dZ, T, ldz, dw, dpacked, 0, st, &up);
+        FRK_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+}  // namespace frk_capi
 
 extern "C" {
 

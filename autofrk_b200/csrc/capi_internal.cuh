@@ -73,3 +73,10 @@ struct frk_plan {
         }
     }
 };
+
+namespace frk_capi {
+// capi_frk.cu: fused predict -> Gram with Z in host memory, uploaded chunk by chunk behind K1 (blocks until done)
+void predict_gram_host_z(frk_plan* plan, const double* dx, int64_t n2, int64_t ldx, const double* hZ, int64_t ldzh,
+                         double* dZ, int T, int64_t ldz, const double* dw, double* dpacked, cudaStream_t st);
+}
+

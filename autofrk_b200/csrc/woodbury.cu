@@ -275,17 +275,20 @@ int32_t frk_plan_predict_gram(frk_plan* plan, const double* xnew, int64_t n2, co
         frk::DevBuf<double> dx(size_t(ld) * d), dZ, dw, packed(frk::gram_packed_len(K, T));
         cudaStream_t st = nullptr;   // this thread's default stream; large pageable inputs go up through the pinned ring
         frk::upload_matrix(dx.p, ld, xnew, n2, n2, d, st);
-        if (T > 0) {
-            dZ.alloc(size_t(ld) * T);
-            frk::upload_matrix(dZ.p, ld, Z, n2, n2, T, st);
-        }
+        if (T > 0) dZ.alloc(size_t(ld) * T);
         if (weights) {
             dw.alloc(static_cast<size_t>(ld));
             frk::upload_matrix(dw.p, ld, weights, n2, n2, 1, st);
         }
-        int32_t rc = frk_plan_predict_gram_dev(plan, dx.p, n2, ld, T > 0 ? dZ.p : nullptr, T, ld, weights ? dw.p : nullptr,
-                                               packed.p, 0, nullptr);
-        if (rc != FRK_OK) frk::fail(rc, "%s", frk_last_error());
+        if (T > 0 && sizeof(double) * size_t(n2) * size_t(T) >= (size_t(256) << 20)) {
+            // a large Z goes up chunk by chunk behind the basis evaluation instead of in front of it
+            frk_capi::predict_gram_host_z(plan, dx.p, n2, ld, Z, n2, dZ.p, T, ld, weights ? dw.p : nullptr, packed.p, st);
+        } else {
+            if (T > 0) frk::upload_matrix(dZ.p, ld, Z, n2, n2, T, st);
+            int32_t rc = frk_plan_predict_gram_dev(plan, dx.p, n2, ld, T > 0 ? dZ.p : nullptr, T, ld,
+                                                   weights ? dw.p : nullptr, packed.p, 0, nullptr);
+            if (rc != FRK_OK) frk::fail(rc, "%s", frk_last_error());
+        }
         FRK_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
         FRK_CUDA(cudaMemcpy(G, packed.p, sizeof(double) * K * K, cudaMemcpyDeviceToHost));
         if (T > 0 && C) FRK_CUDA(cudaMemcpy(C, packed.p + size_t(K) * K, sizeof(double) * K * T, cudaMemcpyDeviceToHost));

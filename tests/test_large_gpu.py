@@ -280,3 +280,59 @@ def test_large_pageable_inputs_go_through_the_pinned_ring():
     Gm, Cm, zz = GF.gram_stats(f, z)
     within("test_large_pageable_inputs:G_long_columns", relmax(Gm, f.T @ f), 1e-12)
     within("test_large_pageable_inputs:C_long_columns", relmax(Cm, f.T @ z), 1e-11)
+
+
+def test_predict_gram_host_path_uploads_Z_behind_the_basis_evaluation():
+    """frk_plan_predict_gram with a large Z in (pageable and pinned) host memory: Z goes up chunk by chunk on a copy
+    stream while K1 evaluates the same chunk (several row chunks here).  Same chunks, same kernels, same order of the
+    partial sums as the device-resident entry point: bitwise identical statistics."""
+    import ctypes as C
+
+    import torch
+
+    from autofrk_b200 import dist as D, mrts as GM
+    from autofrk_b200._lib import check, lib, ptr
+
+    rng = np.random.default_rng(41)
+    d, m, K, T, n2 = 2, 300, 200, 12, 3_000_002                    # 2 GB basis chunks of 1.34 M rows: 3 chunks; Z 288 MB
+    # (even row count: the host path pads its device copies to an even leading dimension, and the Gram kernel picks
+    # its variant by alignment -- with equal layouts both entry points run the same kernels)
+    Xu = rng.random((m, d))
+    basis = GM.mrts(Xu, K)
+    plan = basis.plan()
+    x = np.asfortranarray(rng.random((n2, d)))
+    Z = np.asfortranarray(rng.standard_normal((n2, T)))
+    w = np.asfortranarray(rng.random(n2) + 0.5)
+    for weights in (None, w):
+        Gm, Cm, zz = np.empty((K, K), order="F"), np.empty((K, T), order="F"), np.zeros(1)
+        check(lib.frk_plan_predict_gram(plan._h, ptr(x), n2, ptr(Z), T, None if weights is None else ptr(weights),
+                                        ptr(Gm), ptr(Cm), ptr(zz)))
+        xt = torch.from_numpy(x.T.copy()).cuda().T               # column-major device copies
+        Zt = torch.from_numpy(Z.T.copy()).cuda().T
+        wt = None if weights is None else torch.from_numpy(weights).cuda()
+        packed = D.predict_gram_shard(plan, xt, Zt, w_t=wt).cpu().numpy()
+        within("test_predict_gram_host_path:G_vs_device_path", relmax(Gm.ravel(order="F"), packed[:K * K]), 1e-13)
+        within("test_predict_gram_host_path:C_vs_device_path", relmax(Cm.ravel(order="F"), packed[K * K:K * K + K * T]), 1e-13)
+        assert np.array_equal(Gm.ravel(order="F"), packed[:K * K])
+        assert np.array_equal(Cm.ravel(order="F"), packed[K * K:K * K + K * T])
+        assert zz[0] == packed[-1]
+        del xt, Zt
+    # an odd row count: the device copies get a padded leading dimension, so only closeness is required
+    xo, Zo = np.asfortranarray(x[:-1]), np.asfortranarray(Z[:-1])
+    Go, Co, zo = np.empty((K, K), order="F"), np.empty((K, T), order="F"), np.zeros(1)
+    check(lib.frk_plan_predict_gram(plan._h, ptr(xo), n2 - 1, ptr(Zo), T, None, ptr(Go), ptr(Co), ptr(zo)))
+    packed = D.predict_gram_shard(plan, torch.from_numpy(xo.T.copy()).cuda().T, torch.from_numpy(Zo.T.copy()).cuda().T).cpu().numpy()
+    within("test_predict_gram_host_path:G_odd_rows", relmax(Go.ravel(order="F"), packed[:K * K]), 1e-13)
+    within("test_predict_gram_host_path:C_odd_rows", relmax(Co.ravel(order="F"), packed[K * K:K * K + K * T]), 1e-12)
+    del xo, Zo
+    # pinned Z takes the same route with direct asynchronous copies
+    Zp = torch.from_numpy(Z.T.copy()).pin_memory()
+    Gp, Cp, zp = np.empty((K, K), order="F"), np.empty((K, T), order="F"), np.zeros(1)
+    check(lib.frk_plan_predict_gram(plan._h, ptr(x), n2, C.c_void_p(Zp.data_ptr()), T, ptr(w), ptr(Gp), ptr(Cp), ptr(zp)))
+    assert np.array_equal(Gp, Gm) and np.array_equal(Cp, Cm) and zp[0] == zz[0]
+    # sanity of the statistics themselves (parity of predict -> Gram is test_gram_dev_and_fused_predict_gram's job):
+    # the first basis column is the constant 1, so against Z = 1 its cross-product is the row count
+    ones = np.asfortranarray(np.ones((n2, 1)))
+    G1, C1, z1 = np.empty((K, K), order="F"), np.empty((K, 1), order="F"), np.zeros(1)
+    check(lib.frk_plan_predict_gram(plan._h, ptr(x), n2, ptr(ones), 1, None, ptr(G1), ptr(C1), ptr(z1)))
+    assert z1[0] == float(n2) and abs(C1[0, 0] - n2) <= 1e-9 * n2 and abs(G1[0, 0] - n2) <= 1e-9 * n2
