@@ -19,7 +19,8 @@
 //   * no CTA-wide barrier inside a work item: a 6-deep stage ring, `full` mbarriers, and the warp that is last
 //     to finish with a stage (shared counter) re-arms it, one TMA per lane;
 //   * persistent CTAs pull (row split, job) items from a global counter, split-major so that CTAs running
-//     together read the same rows of F through L2; jobs are ordered longest first;
+//     together read the same rows of F through L2 (items of a few thousand rows when there are many jobs, so that
+//     they stay together); jobs are ordered longest first;
 //   * every item writes its tiles to a workspace and a second kernel adds them in a fixed order (bitwise
 //     reproducible, no atomics) and mirrors G.
 #include <algorithm>
@@ -562,8 +563,14 @@ void gram_stats_tma_dev(const double* dF, int64_t n, int K, int64_t ldf, const d
     }();
     auto round_rows = [kr](int64_t r) { return std::max<int64_t>(kr, (r + kr - 1) / kr * kr); };
     const int64_t max_split = std::max<int64_t>(1, n / 2048);
-    if (a.njobs == 1 || items_env > 0 || max_split < 16) {
-        const int per_cta = (a.njobs == 1) ? 1 : (items_env > 0 ? items_env : 6);
+    // Many jobs over many rows (K = 500: 13 jobs re-reading the same 20 column blocks): short items keep the CTAs that
+    // run together within a few thousand rows of each other, so the re-reads hit L2 instead of HBM -- at n = 5e6,
+    // K = 500, T = 100 dram__bytes_read falls from 82.8 GB (3.45 x algorithmic) to 37.4 GB at the same 56 ms
+    // (profiles/gram_items_probe_r02.txt); the price is 1.7 GB of partial tiles.  With few jobs there is little
+    // to re-read and short items only add epilogues (K = 200, T = 20: +5%), so those keep the two-level split.
+    const bool short_items = a.njobs >= 8 && n >= (int64_t(1) << 20);
+    if (a.njobs == 1 || items_env > 0 || max_split < 16 || short_items) {
+        const int per_cta = (a.njobs == 1) ? 1 : (items_env > 0 ? items_env : (short_items ? 96 : 6));
         a.nsplit = int(std::max<int64_t>(1, std::min<int64_t>(max_split, (int64_t(sms) * per_cta + a.njobs - 1) / a.njobs)));
         a.nsplit_big = a.nsplit;
         a.rows_big = a.rows_small = round_rows((n + a.nsplit - 1) / a.nsplit);
