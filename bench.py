@@ -638,14 +638,19 @@ def fit_benchmarks(torch, dist, world, rank, basis, x, args, dgemm_peak):
                               s=0.0, wSave=True, onlylogLike=False, K=K, on_device=True)
         t2 = time.perf_counter()
         # the same collective through NCCL, timed on the same buffer (first-class path, also the fallback)
-        nccl_ms = None
+        # and both collectives timed alone on ranks that arrive together (best of 3 back-to-back calls): collective_ms
+        # above also holds the wait for the slowest rank's predict_gram
+        nccl_ms, peer_ms = None, None
         if world > 1:
             buf = packed.clone()
             nccl_ms = timed(torch, lambda: dist.all_reduce(buf, op=dist.ReduceOp.SUM), 3)
+            if peer is not None:
+                dist.barrier()
+                peer_ms = timed(torch, lambda: peer(), 3)
         gram_flops = rows * (K * (K + 1.0) + 2.0 * K * T + 2.0 * T)
         out["cmle_sharded"].append({
             "rows_per_gpu": rows, "K": K, "T": T, "predict_gram_ms": e0.elapsed_time(e1), "collective_ms": e1.elapsed_time(e2),
-            "nccl_allreduce_ms": nccl_ms, "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
+            "nccl_allreduce_ms": nccl_ms, "peer_sum_ms": peer_ms, "kxk_stage_ms": (t2 - t1) * 1e3, "wall_ms": (t2 - t0) * 1e3, "v": res["v"],
             "collective": "none (1 GPU)" if world == 1 else ("frk_peer_sum_dev over NVLink peer memory" if peer is not None
                                                             else "NCCL all_reduce"),
             "check": check, "collective_fallback_reason": fallback,

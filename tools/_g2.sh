@@ -7,5 +7,5 @@ import json
 b=json.load(open("gpurun_out/bench_r02_n$N.json"))
 print("value",b["value"],"ms",b["ms_per_step"],"e2e",b["e2e"]["value"],"pageable",b["e2e"]["pageable"]["value"])
 print("fused",{k:v["value"] for k,v in b["e2e"]["fused"].items() if isinstance(v,dict)})
-for c in b["fit"]["cmle_sharded"]: print({k:c[k] for k in ("T","predict_gram_ms","collective_ms","nccl_allreduce_ms","kxk_stage_ms","wall_ms","collective","check","collective_fallback_reason")})
+for c in b["fit"]["cmle_sharded"]: print({k:c[k] for k in ("T","predict_gram_ms","collective_ms","nccl_allreduce_ms","peer_sum_ms","kxk_stage_ms","wall_ms","collective","check","collective_fallback_reason")})
 PY
