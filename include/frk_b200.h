@@ -23,6 +23,10 @@
  * overlap of two calls that share a workspace -- use two host threads (and two plans) for that.
  * Limits: dimensions are int64_t / int32_t as declared; n2 < 2^31 rows per call for the TMA-staged Gram kernels
  * (larger inputs take the cp.async kernel); knots m <= 65535 (the reference caps them at maxknot = 5000).
+ * Device memory a calling thread keeps between calls: the Gram workspace (partial tiles; up to about 1.9 GB once a
+ * Gram with K >= ~250 over >= 2^20 rows has run), and per plan the 2 GB basis chunk of the fused predict -> Gram /
+ * predict.FRK paths; host memory: two 128 MB pinned staging slots per thread that uploads pageable matrices and two
+ * pinned result chunks per plan that returns a basis to pageable memory.
  */
 #ifndef FRK_B200_H
 #define FRK_B200_H
