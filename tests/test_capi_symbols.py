@@ -113,3 +113,20 @@ def test_gram_mid_plan_covers_every_tile_once_and_balances_the_pipes():
             assert len(set(holders)) == cnt and all(0 <= w < 16 // ns.value and 0 <= s < 16 for w, s in holders), (K, T)
             assert ns.value in (1, 2, 4) and sum(sp) == cnt * ns.value
             assert max(sp) - min(sp) <= 2, (K, T, list(sp))
+
+
+def test_k1_traffic_record_was_captured_from_the_committed_kernel_sources():
+    """bench.py reports roofline.traffic from profiles/k1_traffic_r02.json only while the SHA-256 of the K1 sources
+    equals the one recorded at capture time (tools/k1_traffic_capture.py).  The committed record must match the
+    committed sources -- otherwise the driver-run line would carry traffic = null."""
+    import json
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    import bench
+
+    rec = json.loads((root / "profiles" / "k1_traffic_r02.json").read_text())
+    assert rec["k1_sources"] == list(bench.K1_SOURCES)
+    assert rec["k1_sources_sha256"] == bench.sources_sha256(bench.K1_SOURCES)
+    assert 0.9 < rec["traffic_bytes"] / rec["algorithmic_bytes"] < 1.1
