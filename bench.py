@@ -23,7 +23,7 @@ import time
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
-if "reference" in sys.argv or os.environ.get("WORLD_SIZE", "1") == "1":
+if __name__ == "__main__" and ("reference" in sys.argv or os.environ.get("WORLD_SIZE", "1") == "1"):
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core (set before numpy loads OpenBLAS)
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
