@@ -1,3 +1,4 @@
+# N-GPU sequence on the GPU box: `gpurun --gpus N -- "bash tools/_g2.sh N"` (sharded-fit tests, then the bench under torchrun)
 cd $GRAFT_REPO_ROOT
 N=$1
 python -m pytest tests/test_dist_gpu.py tests/test_large_gpu.py -q -m gpu > gpurun_out/r2_dist_n$N.log 2>&1; tail -4 gpurun_out/r2_dist_n$N.log
