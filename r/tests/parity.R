@@ -3,8 +3,8 @@
 ##   Rscript parity.R dump stock.rds      # in a library that holds egpivo/autoFRK 1.4.4
 ##   Rscript parity.R dump overlay.rds    # in a library that holds the package with r/ applied (FRK_B200_HOME set)
 ##   Rscript parity.R compare stock.rds overlay.rds
-## The cases are the reference's own examples (man/mrts.Rd:26-35, man/autoFRK.Rd:85-140, man/predict.FRK.Rd) plus the
-## three kernel dimensions; tolerances as in tests/: 1e-10 column-max-relative, eigen-columns up to sign.
+## The cases follow the shape of the reference's documented examples (a 30 x 30 grid, 150 sites, 20 replicates; knots
+## in d = 1, 2, 3), generated here; tolerances as in tests/: 1e-10 column-max-relative, eigen-columns up to sign.
 args <- commandArgs(trailingOnly = TRUE)
 
 colrel <- function(a, b) {            # max over columns of max|a - b| / max|b|, columns of `a` sign-aligned to `b`
@@ -29,17 +29,15 @@ dump <- function(path) {
     out[[paste0("mrts_d", d)]] <- list(X = unclass(B)[, ], UZ = attr(B, "UZ"), BBBH = attr(B, "BBBH"),
                                        nconst = attr(B, "nconst"), pred = unclass(predict(B, newx))[, ])
   }
-  originalPar <- NULL
-  n <- 150; s <- 5; grid1 <- grid2 <- seq(0, 1, l = 30); grids <- expand.grid(grid1, grid2)
-  fn <- matrix(0, 900, 2)
-  fn[, 1] <- cos(sqrt((grids[, 1] - 0)^2 + (grids[, 2] - 1)^2) * pi)
-  fn[, 2] <- cos(sqrt((grids[, 1] - 0.75)^2 + (grids[, 2] - 0.25)^2) * 2 * pi)
-  wt <- matrix(0, 2, 20)
-  for (tt in 1:20) wt[, tt] <- c(rnorm(1, sd = 5), rnorm(1, sd = 3))
-  yt <- fn %*% wt
-  obs <- sample(900, n)
-  zt <- yt[obs, ] + matrix(rnorm(n * 20), n, 20) * sqrt(s)
-  X <- grids[obs, ]
+  ## a smooth two-component field on the unit square, 20 replicates with random amplitudes, 150 noisy sites
+  side <- seq(0, 1, length.out = 30)
+  grids <- as.matrix(expand.grid(side, side))
+  bump <- function(cx, cy, freq) cos(freq * pi * sqrt((grids[, 1] - cx)^2 + (grids[, 2] - cy)^2))
+  field <- cbind(bump(0, 1, 1), bump(0.75, 0.25, 2))
+  amp <- rbind(rnorm(20, sd = 5), rnorm(20, sd = 3))
+  sites <- sample(nrow(grids), 150)
+  zt <- (field %*% amp)[sites, ] + matrix(rnorm(150 * 20, sd = sqrt(5)), 150, 20)
+  X <- grids[sites, ]
   one <- autoFRK(Data = zt[, 1], loc = X, maxK = 15)                       # R/autoFRK.R:121-197, T = 1
   out$one <- list(K = NCOL(one$G), M = one$M, s = one$s, w = one$w, V = one$V, negloglik = one$negloglik,
                   pred = predict(one, newloc = grids, se.report = TRUE))
