@@ -72,7 +72,7 @@ predict.FRK <- local({
   function(object, obsData = NULL, obsloc = NULL, mu.obs = 0, newloc = obsloc, basis = NULL, mu.new = 0,
            se.report = FALSE, ...) {
     fused <- is.null(object$LKobj) && is.null(obsData) && is.null(obsloc) && is.null(basis) && !is.null(newloc) &&
-      inherits(object$G, "mrts") && !is.null(object$w) && is.null(attr(object, "missing")) &&
+      inherits(object$G, "mrts") && !is.null(object$w) &&
       NCOL(object$G) > NCOL(attr(object$G, "Xu")) + 1
     if (!fused) {
       return(reference_predict.FRK(object, obsData = obsData, obsloc = obsloc, mu.obs = mu.obs, newloc = newloc,
@@ -80,6 +80,30 @@ predict.FRK <- local({
     }
     G <- object$G
     x0 <- matrix(as.double(as.matrix(newloc)), ncol = NCOL(attr(G, "Xu")))
+    miss <- attr(object, "missing")
+    if (!is.null(miss) && se.report) {
+      ## a model fitted through EM0miss: one V per replicate from the rows observed in it (R/autoFRK.R:1224-1245).
+      ## All masked Grams t(G_t) solve(De_t) G_t come from one pass over the basis rows, each V_t is K x K algebra,
+      ## and yhat[, tt], se[, tt] come out of one fused kernel pass per replicate.
+      pinfo <- attr(object, "pinfo")
+      pick <- pinfo$pick
+      D0 <- as.double(diag(pinfo$D))[pick]
+      observed <- 1 - as.matrix(miss$miss)
+      TT <- NCOL(object$w)
+      if (NCOL(observed) < TT) stop("subscript out of bounds")   # miss[, tt] at :1233 when the fit dropped empty replicates
+      Fk <- matrix(as.double(unclass(G)[pick, ]), nrow = length(pick))
+      K <- NCOL(Fk)
+      GG <- .Call(`_autoFRK_masked_grams`, Fk, matrix(as.double(observed), nrow = NROW(observed)), D0)
+      yhat <- se <- matrix(0, NROW(x0), TT)
+      for (tt in 1:TT) {
+        Vt <- .Call(`_autoFRK_krige_V`, matrix(GG[, tt], K, K) / object$s, as.matrix(object$M))
+        res <- .Call(`_autoFRK_predict_frk`, attr(G, "Xu"), attr(G, "BBBH"), attr(G, "UZ"), as.double(attr(G, "nconst")),
+                     as.integer(NCOL(G)), x0, as.matrix(object$w[, tt, drop = FALSE]), Vt)
+        yhat[, tt] <- res$yhat
+        se[, tt] <- res$se
+      }
+      return(list(pred.value = yhat + mu.new, se = se))
+    }
     res <- .Call(`_autoFRK_predict_frk`, attr(G, "Xu"), attr(G, "BBBH"), attr(G, "UZ"), as.double(attr(G, "nconst")),
                  as.integer(NCOL(G)), x0, as.matrix(object$w), if (se.report) as.matrix(object$V) else NULL)
     TT <- NCOL(object$w)

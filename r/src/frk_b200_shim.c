@@ -233,6 +233,43 @@ SEXP _autoFRK_predict_frk(SEXP Xu, SEXP BBBH, SEXP UZ, SEXP nconst, SEXP K_, SEX
     return out;
 }
 
+/* Per-replicate NA-masked weighted Grams of the basis rows (R/autoFRK.R:1233-1235: G <- Fk[!miss[, tt], ],
+ * De <- D0[!miss[, tt], !miss[, tt]]; the same products as EM0miss' BiDBt, :609-615): `observed` is an n x TT matrix of
+ * 0/1 doubles, `Ddiag` = diag(D0).  Returns a (K*K) x TT matrix: column tt holds t(G) solve(De) G, column-major.
+ * One pass over the rows of Fk for all replicates. */
+SEXP _autoFRK_masked_grams(SEXP Fk, SEXP observed, SEXP Ddiag) {
+    need_real_matrix(Fk, "Fk"); need_real_matrix(observed, "observed");
+    R_xlen_t n = nrow_of(Fk); int K = ncol_of(Fk), T = ncol_of(observed);
+    if (TYPEOF(Ddiag) != REALSXP || XLENGTH(Ddiag) != n || nrow_of(observed) != n)
+        Rf_error("observed and Ddiag must have one row per row of Fk");
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, K * K, T));
+    SEXP mask = PROTECT(Rf_allocVector(RAWSXP, n * T));
+    SEXP zero = PROTECT(Rf_allocMatrix(REALSXP, (int)n, T));
+    SEXP rest = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)K * T + 2 * (R_xlen_t)T));   /* c_all | zz_all | nobs_all (int64) */
+    const double *o = REAL(observed);
+    unsigned char *mk = RAW(mask);
+    double *z = REAL(zero);
+    for (R_xlen_t i = 0; i < n * T; ++i) { mk[i] = (o[i] != 0.0); z[i] = 0.0; }
+    double *c_all = REAL(rest), *zz_all = c_all + (R_xlen_t)K * T;
+    check(frk_masked_stats(z, mk, REAL(Fk), REAL(Ddiag), n, K, T, REAL(out), c_all, zz_all, (int64_t *)(zz_all + T)));
+    UNPROTECT(4);
+    return out;
+}
+
+/* V = M - t(G M) invCz(R, L, G M), L = G eigen(M)$vectors diag(sqrt(pmax(eigen(M)$values, 0)))  (R/autoFRK.R:1236-1240,
+ * 1260-1271), as K x K algebra on Gg = t(G) solve(R) G. */
+SEXP _autoFRK_krige_V(SEXP Gg, SEXP M) {
+    need_real_matrix(Gg, "Gg"); need_real_matrix(M, "M");
+    int K = Rf_nrows(M);
+    if (Rf_ncols(M) != K || Rf_nrows(Gg) != K || Rf_ncols(Gg) != K) Rf_error("Gg and M must be K x K");
+    SEXP V = PROTECT(Rf_allocMatrix(REALSXP, K, K));
+    SEXP c = PROTECT(Rf_allocVector(REALSXP, 2 * (R_xlen_t)K));     /* a zero data column and its (unused) coefficients */
+    for (int i = 0; i < 2 * K; ++i) REAL(c)[i] = 0.0;
+    check(frk_krige_from_stats(REAL(Gg), REAL(c), 1, REAL(M), K, 1, REAL(c) + K, REAL(V)));
+    UNPROTECT(2);
+    return V;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_getASCeigens", (DL_FUNC)&_autoFRK_getASCeigens, 1},
     {"_autoFRK_mrtsrcpp", (DL_FUNC)&_autoFRK_mrtsrcpp, 3},
@@ -245,6 +282,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_autoFRK_predict_mrts_basis", (DL_FUNC)&_autoFRK_predict_mrts_basis, 6},
     {"_autoFRK_predict_gram", (DL_FUNC)&_autoFRK_predict_gram, 7},
     {"_autoFRK_predict_frk", (DL_FUNC)&_autoFRK_predict_frk, 8},
+    {"_autoFRK_masked_grams", (DL_FUNC)&_autoFRK_masked_grams, 3},
+    {"_autoFRK_krige_V", (DL_FUNC)&_autoFRK_krige_V, 2},
     {NULL, NULL, 0}};
 
 void R_init_autoFRK(DllInfo *dll) {

@@ -14,6 +14,7 @@ extern SEXP R_NamesSymbol;
 extern SEXP R_NilValue;
 #define NILSXP 0
 #define LGLSXP 10
+#define RAWSXP 24
 int TYPEOF(SEXP);
 Rboolean Rf_isMatrix(SEXP);
 R_xlen_t XLENGTH(SEXP);
@@ -21,6 +22,7 @@ int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
 double *REAL(SEXP);
 int *INTEGER(SEXP);
+unsigned char *RAW(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
 SEXP Rf_mkChar(const char *);

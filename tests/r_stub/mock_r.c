@@ -40,7 +40,7 @@ static SEXP new_obj(int type, R_xlen_t len, size_t elt) {
     return s;
 }
 static size_t elt_size(unsigned type) {
-    return type == REALSXP ? sizeof(double) : (type == INTSXP || type == LGLSXP) ? sizeof(int) : sizeof(SEXP);
+    return type == REALSXP ? sizeof(double) : (type == INTSXP || type == LGLSXP) ? sizeof(int) : type == RAWSXP ? 1 : sizeof(SEXP);
 }
 
 int TYPEOF(SEXP x) { return x->type; }
@@ -55,6 +55,10 @@ double *REAL(SEXP x) {
 int *INTEGER(SEXP x) {
     if (x->type != INTSXP && x->type != LGLSXP) Rf_error("INTEGER() can only be applied to a 'integer', not a type-%d object", x->type);
     return (int *)x->data;
+}
+unsigned char *RAW(SEXP x) {
+    if (x->type != RAWSXP) Rf_error("RAW() can only be applied to a 'raw', not a type-%d object", x->type);
+    return (unsigned char *)x->data;
 }
 SEXP Rf_allocVector(unsigned type, R_xlen_t n) { return new_obj((int)type, n, elt_size(type)); }
 SEXP Rf_allocMatrix(unsigned type, int nr, int nc) {

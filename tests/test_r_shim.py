@@ -46,7 +46,8 @@ def test_registration_table_matches_the_reference():
         assert mine.get(name) == nargs, (name, nargs, mine.get(name))
     extra = set(mine) - set(ref["call_entries"])
     assert extra == {"_autoFRK_gram_stats", "_autoFRK_getHalf_stats", "_autoFRK_cMLEimat_stats", "_autoFRK_cMLEimat_sweep",
-                     "_autoFRK_predict_mrts_basis", "_autoFRK_predict_gram", "_autoFRK_predict_frk"}
+                     "_autoFRK_predict_mrts_basis", "_autoFRK_predict_gram", "_autoFRK_predict_frk",
+                     "_autoFRK_masked_grams", "_autoFRK_krige_V"}
     # every .Call in the overlay's R code names a registered routine and passes its registered number of arguments
     rsrc = (ROOT / "r" / "R" / "overrides.R").read_text()
     calls = re.findall(r"\.Call\(`(_autoFRK_\w+)`", rsrc)

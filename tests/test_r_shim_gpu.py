@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from r_shim_util import MockR
-from util import TOL, colrel, relmax
+from util import TOL, colrel, relmax, within
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -124,3 +124,36 @@ def test_overlay_routines_match_the_python_mirror(R):
     assert np.array_equal(pr["yhat"], want["pred.value"]) and np.array_equal(pr["se"], want["se"][:, 0])
     pr2 = R.call("_autoFRK_predict_frk", *attrs, R.mat(x[:10]), R.mat(ref["w"]), R.nil())
     assert pr2["se"] is None and np.array_equal(pr2["yhat"], pr["yhat"][:10])
+
+
+def test_masked_grams_and_krige_V_behind_the_per_replicate_se(R):
+    """The two routines the overlay's predict.FRK uses for a model fitted with missing data (R/autoFRK.R:1224-1245):
+    every replicate's t(G_t) solve(De_t) G_t from one pass, and V_t = M - t(G_t M) invCz(s De_t, L_t, G_t M) as K x K
+    algebra -- against the dense definitions."""
+    rng = np.random.default_rng(21)
+    n, K, T = 2500, 9, 4
+    F = rng.standard_normal((n, K))
+    obs = rng.random((n, T)) > 0.3
+    D = rng.random(n) + 0.5
+    GG = R.call("_autoFRK_masked_grams", R.mat(F), R.mat(obs.astype(float)), R.vec(D))
+    assert GG.shape == (K * K, T)
+    for t in range(T):
+        o = obs[:, t]
+        want = (F[o].T / D[o]) @ F[o]
+        assert relmax(GG[:, t].reshape((K, K), order="F"), want) < 1e-12
+    A = rng.standard_normal((K, K))
+    M = A @ A.T / K + 0.1 * np.eye(K)
+    s = 0.7
+    Vt = R.call("_autoFRK_krige_V", R.mat(GG[:, 0].reshape((K, K), order="F") / s), R.mat(M))
+    o = obs[:, 0]
+    G0 = F[o]
+    Cm = np.diag(s * D[o]) + G0 @ M @ G0.T                      # M is positive definite here: M+ = M
+    want = M - M @ G0.T @ np.linalg.solve(Cm, G0 @ M)
+    # V = M - (...) cancels (|V| ~ s / n against |M| ~ 1, and t(G) C^-1 G itself is a difference of terms ~ n / s:
+    # SURVEY 8c (3)), in the reference's formula as much as here
+    assert Vt.shape == (K, K)
+    within("test_masked_grams_and_krige_V:V_vs_dense", relmax(Vt, want), 2e-7)   # observed 1.6e-08 on B200
+    with pytest.raises(RuntimeError, match="one row per row of Fk"):
+        R.call("_autoFRK_masked_grams", R.mat(F), R.mat(obs[:-1].astype(float)), R.vec(D))
+    with pytest.raises(RuntimeError, match="must be K x K"):
+        R.call("_autoFRK_krige_V", R.mat(M[:, :-1]), R.mat(M))
