@@ -130,3 +130,22 @@ def test_k1_traffic_record_was_captured_from_the_committed_kernel_sources():
     assert rec["k1_sources"] == list(bench.K1_SOURCES)
     assert rec["k1_sources_sha256"] == bench.sources_sha256(bench.K1_SOURCES)
     assert 0.9 < rec["traffic_bytes"] / rec["algorithmic_bytes"] < 1.1
+
+
+def test_library_is_sm100a_code_with_fp64_tensor_and_tma_instructions():
+    """The shipped binary is what DESIGN.md says it is: sm_100a cubins only, FP64 tensor-core instructions
+    (DMMA.8x8x4; tcgen05/TMEM have no f64 kind), TMA bulk and tensor copies (UBLKCP, UTMALDG) and mbarrier traffic."""
+    import shutil
+    import subprocess
+
+    import pytest
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    lib = Path(__file__).resolve().parent.parent / "autofrk_b200" / "libfrk_b200.so"
+    sass = subprocess.run([cuobjdump, "-sass", str(lib)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    assert sass.count("DMMA.8x8x4") > 1000
+    assert "UBLKCP.S.G" in sass and "UTMALDG.2D" in sass and "SYNCS.ARRIVE.TRANS64" in sass
